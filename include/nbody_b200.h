@@ -1,0 +1,177 @@
+/*
+ * nbody_b200 — C ABI of the B200 (sm_100a) N-body hot path.
+ *
+ * Drop-in boundary for the one hot path of dasbd72/NTHU_IPC_Nbody-Simulation: the all-pairs FP64
+ * softened-gravity step with sin-modulated gravity-device masses + explicit v/q update, iterated
+ * 200 000 times, and the three queries built on it.  Every entry point names the reference
+ * interface it replaces (file:line into the reference tree).
+ *
+ * Conventions:
+ *   - extern "C", POD structs, plain pointers and sizes; no exceptions cross the boundary;
+ *   - every function returns NB_OK (0) or a negative NB_ERR_* code; nb_strerror() explains it and
+ *     nb_last_error_detail() holds the CUDA error text of the calling thread's last failure;
+ *   - host arrays are owned by the caller; device memory is owned by the library behind opaque
+ *     handles; one handle = one GPU = one stream; handles may be used from different host threads
+ *     concurrently (no global mutable state besides per-GPU lazily built constant tables);
+ *   - planar layout of hw5.cu:93-97: q[3*n] = x block, y block, z block (same for v);
+ *   - there is NO CPU fallback: without a usable GPU every compute call returns NB_ERR_NO_GPU.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_OK 0
+#define NB_ERR_ARG (-1)         /* bad argument (null pointer, n <= 0, index out of range, ...) */
+#define NB_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed; see nb_last_error_detail() */
+#define NB_ERR_NO_GPU (-3)      /* no CUDA device / requested ordinal does not exist              */
+#define NB_ERR_UNSUPPORTED (-4) /* size or mode outside what this build supports                  */
+#define NB_ERR_IO (-5)          /* file could not be read / written / parsed                      */
+
+/* arithmetic of the pair term (nbody.cc:65-72) */
+#define NB_MATH_FAST 0   /* FMA r^2, rsqrt seed + cubic correction (<= 2^-52 rel.), FMA accumulate, j split over lanes */
+#define NB_MATH_STRICT 1 /* IEEE only: sqrt(r2*r2*r2), ((G*mj)*d)/dist3, no FMA, ascending j (== hw5.cu:200-203 form of nbody.cc) */
+
+/* trajectory kinds = the observers that run after every step */
+#define NB_KIND_PLAIN 0 /* min distance only, never stops early                               */
+#define NB_KIND_Q1 1    /* nbody.cc:106-122: devices massless, min planet-asteroid distance    */
+#define NB_KIND_Q2 2    /* nbody.cc:124-138 + hw5.cu:265-287: first hit step, missile reach steps; stops at the hit */
+#define NB_KIND_Q3 3    /* hw5.cu:289-309: hit test, then missile destroys `destroy_device`; stops at the hit */
+
+#define NB_MAX_DEVICES 64
+#define NB_MAX_SMALL_N 1024 /* largest system the persistent (shared-memory resident) kernels take */
+
+/* physics constants of nbody.cc:9-20 (read-only; exported for callers that need them) */
+#define NB_N_STEPS 200000
+#define NB_DT 60.0
+#define NB_EPS 1e-3
+#define NB_G 6.674e-11
+#define NB_PLANET_RADIUS 1e7
+#define NB_MISSILE_SPEED 1e6
+
+typedef struct nb_system {
+    int n;                          /* bodies                                        */
+    int planet;                     /* index of the planet   (input header, nbody.cc:27) */
+    int asteroid;                   /* index of the asteroid                         */
+    const double* q;                /* [3*n] planar positions                        */
+    const double* v;                /* [3*n] planar velocities                       */
+    const double* m;                /* [n] base masses                               */
+    const unsigned char* is_device; /* [n] 1 where type == "device" (nbody.cc:62)    */
+} nb_system;
+
+typedef struct nb_events {
+    double min_d2;      /* min over observed steps of d^2(planet, asteroid) (hw5.cu:241-252)          */
+    int argmin_step;    /* first step attaining it                                                    */
+    int hit_step;       /* first step with d^2 < planet_radius^2 (nbody.cc:134), else -2              */
+    int destroyed_step; /* Q3: step at which the missile reached the device (hw5.cu:299-307), else -2 */
+    double cost;        /* Q3: 1e5 + 1e3*((destroyed_step+1)*dt) (hw5.cu:305), else +inf              */
+    int steps_done;     /* step the state is at (== hit step when stopped early); -1 = not yet observed */
+    int n_reach;        /* number of devices                                                          */
+    int reach_step[NB_MAX_DEVICES]; /* Q2: first step with d^2(planet, device k) < (1e6*60*step)^2, else -2 (hw5.cu:265-287) */
+} nb_events;
+
+typedef struct nb_answer {
+    double min_dist;       /* output line 1 (nbody.cc:44-48) */
+    int hit_time_step;     /* output line 2; -2 = no hit     */
+    int gravity_device_id; /* output line 3; -1 = none       */
+    double missile_cost;   /* output line 3; 0 when none     */
+    /* diagnostics */
+    int argmin_step;
+    int n_devices;
+    int device_index[NB_MAX_DEVICES];
+    int reach_step[NB_MAX_DEVICES];
+    int q3_hit_step[NB_MAX_DEVICES]; /* -2 = planet saved, -3 = not simulated, else hit step */
+    double q3_cost[NB_MAX_DEVICES];
+    double gpu_seconds;   /* max over GPUs of the device time spent in trajectory kernels */
+    double wall_seconds;  /* host wall time inside nb_solve, context creation included   */
+    long long pair_interactions; /* ordered pair interactions evaluated                  */
+    int n_trajectories;
+    int n_gpus_used;
+} nb_answer;
+
+/* ---- library / device ------------------------------------------------------------------- */
+const char* nb_version(void);
+const char* nb_strerror(int code);
+const char* nb_last_error_detail(void); /* thread-local text of the last NB_ERR_CUDA */
+int nb_device_count(int* count);        /* NB_ERR_NO_GPU when there is none          */
+/* launches of this library's kernels made by the calling process so far (for bench accounting) */
+long long nb_kernel_launches(void);
+
+/* ---- the step operator -------------------------------------------------------------------
+ * Replaces run_step(step, n, qx,qy,qz, vx,vy,vz, m, type) (nbody.cc:51-89) and the kernel pair
+ * compute_accelerations_gpu + update_positions_gpu (hw5.cu:159-215, 231-239): advances the
+ * caller's HOST arrays q, v in place by the steps step_begin+1 .. step_end (run_step's `step`
+ * argument takes each of those values).  Any n >= 1.  `m` are base masses; device modulation
+ * (nbody.cc:14-16) is applied inside.
+ */
+int nb_run_steps(int gpu, int math, int n, double* q, double* v, const double* m,
+                 const unsigned char* is_device, int step_begin, int step_end);
+
+/* ---- trajectories (query drivers' inner loops) --------------------------------------------
+ * Replaces the host-driven loops of t_problem_12 / t_problem_3 (hw5.cu:322-436, 438-530): one
+ * persistent kernel runs every step and every observer on the GPU.  n <= NB_MAX_SMALL_N.
+ */
+typedef struct nb_traj nb_traj;
+int nb_traj_create(int gpu, const nb_system* sys, int kind, int destroy_device, int math, nb_traj** out);
+/* run from the current step up to and including step_end, or until the kind's stop event */
+int nb_traj_run(nb_traj* t, int step_end, nb_events* ev);
+/* current state (any pointer may be NULL); m = base masses as the trajectory now sees them */
+int nb_traj_state(nb_traj* t, double* q, double* v, double* m, int* step);
+/* fork: a new trajectory of `kind` starting from t's current state (hw5.cu:275-284 snapshot, :482-483 restore) */
+int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out);
+int nb_traj_destroy(nb_traj* t);
+
+/* ---- ensembles ------------------------------------------------------------------------------
+ * n_systems independent systems of the same n in one launch, one thread block per system
+ * (north-star (c): batches of synthetic systems).  Arrays are system-major: q[s][3*n] ...
+ * planet/asteroid/destroy_device are per system.  q, v are updated in place; ev[s] filled.
+ */
+int nb_ensemble_run(int gpu, int math, int kind, int n_systems, int n, double* q, double* v,
+                    const double* m, const unsigned char* is_device, const int* planet,
+                    const int* asteroid, const int* destroy_device, int step_begin, int step_end,
+                    nb_events* ev, double* gpu_seconds);
+
+/* ---- the three queries ----------------------------------------------------------------------
+ * Replaces main() of hw5.cu:532-616 minus file I/O: Q1, Q2 and one Q3 trajectory per device,
+ * scheduled over the given GPUs with no collective (hw5.cu:566-567, 587-588 hard-code two).
+ * gpus == NULL means ordinals 0..n_gpus-1.
+ */
+int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int math, nb_answer* ans);
+
+/* ---- file formats (nbody.cc:22-49, hw5.cu:86-141) ------------------------------------------- */
+int nb_read_header(const char* path, int* n, int* planet, int* asteroid);
+int nb_read_input(const char* path, int max_n, int* n, int* planet, int* asteroid, double* q,
+                  double* v, double* m, unsigned char* is_device);
+int nb_write_output(const char* path, double min_dist, int hit_time_step, int gravity_device_id,
+                    double missile_cost);
+/* the whole CLI: hw5 <input> <output> (hw5.cu:532-616) */
+int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus);
+
+/* ---- large systems, body-sharded (north-star (d)) -------------------------------------------
+ * DEVICE-pointer interface: the caller (C++ or torch) owns the buffers and the stream, so that a
+ * per-step position all-gather (NCCL) can run between calls on the same stream.
+ *   pos4     [n][4] doubles  {x, y, z, G*m_eff(step)} of ALL bodies at the current step
+ *   pos4_out [n][4] doubles  rows i_begin..i_begin+i_count-1 are written with the state after the
+ *                            step and G*m_eff(step+1); other rows untouched (peers fill them)
+ *   vel      [3][i_count]    planar velocities of the local bodies, updated in place
+ *   m0       [n] base masses, is_device [n]
+ *   scratch  nb_large_scratch_bytes() bytes
+ */
+long long nb_large_scratch_bytes(int n, int i_count);
+int nb_large_pack(int math, int n, const double* q_planar_dev, const double* m0_dev,
+                  const unsigned char* is_device_dev, int step_next, double* pos4_dev, void* stream);
+int nb_large_unpack(int n, const double* pos4_dev, double* q_planar_dev, void* stream);
+int nb_large_step(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev,
+                  double* pos4_out_dev, double* vel_dev, const double* m0_dev,
+                  const unsigned char* is_device_dev, void* scratch_dev, void* stream);
+
+/* ---- measurement helpers ----------------------------------------------------------------------- */
+/* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */
+int nb_fp64_peak(int gpu, double* tflops, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,493 @@
+// C ABI of libnbody_b200.so: device plumbing, trajectory handles, ensembles, the three-query
+// driver and its ensemble scheduler.  Host code is C++ in the .cu translation unit, as the
+// reference's is (hw5.cu:311-616); the kernels live in nb_traj.cu / nb_grid.cu / nb_large.cu.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "nb_internal.h"
+
+namespace nb {
+
+// ---- errors / counters ---------------------------------------------------------------------------
+static thread_local std::string g_detail;
+void set_error_detail(const std::string& s) { g_detail = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s:%d)", cudaGetErrorString(e), what, file, line);
+    g_detail = buf;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return NB_ERR_NO_GPU;
+    return NB_ERR_CUDA;
+}
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
+
+// ---- |sin(step*dt/6000)| table ----------------------------------------------------------------------
+// nbody.cc:14-16 with t = step*dt (nbody.cc:63): fabs(sin((step*60.0)/6000)), host glibc sin, so the
+// modulation is the oracle's to the bit whatever the device sin() does.  (The reference's own table,
+// hw5.cu:143-148,555, is one entry short and built with the device sin.)
+static std::mutex g_fst_mu;
+static std::vector<double> g_fst_host;
+struct FstDev {
+    double* ptr = nullptr;
+    int len = 0;
+};
+static FstDev g_fst_dev[64];
+
+const double* fst_table_host(int min_len) {
+    std::lock_guard<std::mutex> lk(g_fst_mu);
+    if ((int)g_fst_host.size() < min_len) {
+        int len = min_len < NB_N_STEPS + 1 ? NB_N_STEPS + 1 : min_len;
+        // grow without moving entries other threads may be reading: reserve generously once
+        std::vector<double> t(len);
+        for (int s = 0; s < len; s++) t[s] = fabs(sin((s * NB_DT) / 6000));
+        g_fst_host.swap(t);
+    }
+    return g_fst_host.data();
+}
+
+int fst_table(int gpu, int min_len, const double** out) {
+    if (gpu < 0 || gpu >= 64) return NB_ERR_ARG;
+    const double* h = fst_table_host(min_len);
+    std::lock_guard<std::mutex> lk(g_fst_mu);
+    FstDev& d = g_fst_dev[gpu];
+    if (d.len < min_len) {
+        int len = (int)g_fst_host.size();
+        h = g_fst_host.data();
+        double* p = nullptr;
+        NB_CUDA(cudaSetDevice(gpu));
+        NB_CUDA(cudaMalloc(&p, (size_t)len * sizeof(double)));
+        NB_CUDA(cudaMemcpy(p, h, (size_t)len * sizeof(double), cudaMemcpyHostToDevice));
+        // the old table (if any) is leaked on purpose: a running kernel may still read it
+        d.ptr = p;
+        d.len = len;
+    }
+    *out = d.ptr;
+    return NB_OK;
+}
+
+static int check_gpu(int gpu) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        (void)cudaGetLastError();
+        set_error_detail(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        return NB_ERR_NO_GPU;
+    }
+    if (gpu < 0 || gpu >= cnt) {
+        set_error_detail("GPU ordinal out of range");
+        return NB_ERR_NO_GPU;
+    }
+    return NB_OK;
+}
+
+// ---- a batch of same-n systems resident on one GPU ---------------------------------------------------
+struct DeviceBatch {
+    int gpu = -1, S = 0, n = 0, math = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double *q = nullptr, *v = nullptr, *m = nullptr;
+    unsigned char* isdev = nullptr;
+    int* devidx = nullptr;
+    nb_events* ev = nullptr;
+    TrajDesc* descs = nullptr;
+    void* grid_ws = nullptr;
+    size_t grid_ws_bytes = 0;
+    std::vector<TrajDesc> h_descs;
+    std::vector<nb_events> h_ev;
+    std::vector<int> cur_step;
+    double gpu_seconds = 0.0;
+    long long pairs = 0;
+
+    int init(int gpu_, int S_, int n_, int math_) {
+        gpu = gpu_, S = S_, n = n_, math = math_;
+        NB_CUDA(cudaSetDevice(gpu));
+        NB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        NB_CUDA(cudaEventCreate(&e0));
+        NB_CUDA(cudaEventCreate(&e1));
+        NB_CUDA(cudaMalloc(&q, (size_t)S * 3 * n * sizeof(double)));
+        NB_CUDA(cudaMalloc(&v, (size_t)S * 3 * n * sizeof(double)));
+        NB_CUDA(cudaMalloc(&m, (size_t)S * n * sizeof(double)));
+        NB_CUDA(cudaMalloc(&isdev, (size_t)S * n));
+        NB_CUDA(cudaMalloc(&devidx, (size_t)S * NB_MAX_DEVICES * sizeof(int)));
+        NB_CUDA(cudaMalloc(&ev, (size_t)S * sizeof(nb_events)));
+        NB_CUDA(cudaMalloc(&descs, (size_t)S * sizeof(TrajDesc)));
+        h_descs.assign(S, TrajDesc{});
+        h_ev.assign(S, nb_events{});
+        cur_step.assign(S, 0);
+        return NB_OK;
+    }
+    void release() {
+        if (gpu < 0) return;
+        cudaSetDevice(gpu);
+        cudaFree(q), cudaFree(v), cudaFree(m), cudaFree(isdev), cudaFree(devidx), cudaFree(ev), cudaFree(descs);
+        if (grid_ws) cudaFree(grid_ws);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (stream) cudaStreamDestroy(stream);
+        gpu = -1;
+    }
+    static void fresh_events(nb_events& e) {
+        e.min_d2 = std::numeric_limits<double>::infinity();
+        e.argmin_step = -1;
+        e.hit_step = -2;
+        e.destroyed_step = -2;
+        e.cost = std::numeric_limits<double>::infinity();
+        e.steps_done = -1;
+        e.n_reach = 0;
+        for (int k = 0; k < NB_MAX_DEVICES; k++) e.reach_step[k] = -2;
+    }
+    // upload system s (host pointers), starting at `step0` with nothing observed yet
+    int set_system(int s, const double* hq, const double* hv, const double* hm, const unsigned char* hdev, int planet,
+                   int asteroid, int kind, int destroy_device, int step0) {
+        if (planet < 0 || planet >= n || asteroid < 0 || asteroid >= n) return NB_ERR_ARG;
+        if (kind == NB_KIND_Q3 && (destroy_device < 0 || destroy_device >= n)) return NB_ERR_ARG;
+        std::vector<double> mm(hm, hm + n);
+        std::vector<int> di;
+        for (int i = 0; i < n; i++)
+            if (hdev[i]) {
+                di.push_back(i);
+                if (kind == NB_KIND_Q1) mm[i] = 0.0;  // nbody.cc:109-113, hw5.cu:217-222,357
+            }
+        if ((int)di.size() > NB_MAX_DEVICES) return NB_ERR_UNSUPPORTED;
+        NB_CUDA(cudaSetDevice(gpu));
+        NB_CUDA(cudaMemcpyAsync(q + (size_t)s * 3 * n, hq, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaMemcpyAsync(v + (size_t)s * 3 * n, hv, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaMemcpyAsync(m + (size_t)s * n, mm.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaMemcpyAsync(isdev + (size_t)s * n, hdev, n, cudaMemcpyHostToDevice, stream));
+        if (!di.empty())
+            NB_CUDA(cudaMemcpyAsync(devidx + (size_t)s * NB_MAX_DEVICES, di.data(), di.size() * sizeof(int),
+                                    cudaMemcpyHostToDevice, stream));
+        fresh_events(h_ev[s]);
+        h_ev[s].n_reach = (int)di.size();
+        NB_CUDA(cudaMemcpyAsync(ev + s, &h_ev[s], sizeof(nb_events), cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaStreamSynchronize(stream));  // mm / di are stack-local
+        TrajDesc& d = h_descs[s];
+        d.n = n, d.planet = planet, d.asteroid = asteroid, d.kind = kind, d.destroy_device = destroy_device;
+        d.n_dev = (int)di.size();
+        d.q = q + (size_t)s * 3 * n, d.v = v + (size_t)s * 3 * n, d.m = m + (size_t)s * n;
+        d.is_device = isdev + (size_t)s * n, d.dev_index = devidx + (size_t)s * NB_MAX_DEVICES, d.ev = ev + s;
+        cur_step[s] = step0;
+        return NB_OK;
+    }
+    // advance every system to step_end (or its stop event); blocks until done
+    int run(int step_end, bool allow_grid) {
+        int max_end = step_end;
+        for (int s = 0; s < S; s++) {
+            h_descs[s].step_begin = cur_step[s];
+            h_descs[s].step_end = step_end > cur_step[s] ? step_end : cur_step[s];
+        }
+        const double* fst = nullptr;
+        int rc = fst_table(gpu, max_end + 2, &fst);
+        if (rc) return rc;
+        NB_CUDA(cudaSetDevice(gpu));
+        NB_CUDA(cudaMemcpyAsync(descs, h_descs.data(), S * sizeof(TrajDesc), cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaEventRecord(e0, stream));
+        if (allow_grid && grid_traj_supported(gpu, n, S)) {
+            size_t need = grid_traj_workspace_bytes(n, S);
+            if (need > grid_ws_bytes) {
+                if (grid_ws) NB_CUDA(cudaFree(grid_ws));
+                NB_CUDA(cudaMalloc(&grid_ws, need));
+                grid_ws_bytes = need;
+            }
+            rc = launch_grid_traj(math, n, S, descs, fst, gpu, grid_ws, grid_ws_bytes, stream);
+        } else {
+            rc = launch_traj_batch(math, n, S, descs, fst, stream);
+        }
+        if (rc) return rc;
+        NB_CUDA(cudaEventRecord(e1, stream));
+        NB_CUDA(cudaMemcpyAsync(h_ev.data(), ev, S * sizeof(nb_events), cudaMemcpyDeviceToHost, stream));
+        NB_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        gpu_seconds += ms * 1e-3;
+        for (int s = 0; s < S; s++) {
+            long long steps = h_ev[s].steps_done - cur_step[s];
+            if (steps > 0) pairs += steps * (long long)n * (n - 1);
+            cur_step[s] = h_ev[s].steps_done;
+        }
+        return NB_OK;
+    }
+    int get_state(int s, double* hq, double* hv, double* hm) {
+        NB_CUDA(cudaSetDevice(gpu));
+        if (hq) NB_CUDA(cudaMemcpyAsync(hq, q + (size_t)s * 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (hv) NB_CUDA(cudaMemcpyAsync(hv, v + (size_t)s * 3 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (hm) NB_CUDA(cudaMemcpyAsync(hm, m + (size_t)s * n, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        NB_CUDA(cudaStreamSynchronize(stream));
+        return NB_OK;
+    }
+};
+
+}  // namespace nb
+
+using nb::DeviceBatch;
+
+struct nb_traj {
+    DeviceBatch b;
+    int planet, asteroid, kind, destroy_device;
+    std::vector<unsigned char> isdev;
+};
+
+extern "C" {
+
+const char* nb_version(void) { return "nbody_b200 0.1 (sm_100a)"; }
+
+const char* nb_strerror(int code) {
+    switch (code) {
+        case NB_OK: return "ok";
+        case NB_ERR_ARG: return "invalid argument";
+        case NB_ERR_CUDA: return "CUDA error";
+        case NB_ERR_NO_GPU: return "no usable CUDA device (this library has no CPU fallback)";
+        case NB_ERR_UNSUPPORTED: return "unsupported size or mode";
+        case NB_ERR_IO: return "I/O or parse error";
+        default: return "unknown error";
+    }
+}
+
+const char* nb_last_error_detail(void) { return nb::g_detail.c_str(); }
+
+int nb_device_count(int* count) {
+    if (!count) return NB_ERR_ARG;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess || c == 0) {
+        (void)cudaGetLastError();
+        *count = 0;
+        nb::set_error_detail(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        return NB_ERR_NO_GPU;
+    }
+    *count = c;
+    return NB_OK;
+}
+
+long long nb_kernel_launches(void) { return nb::g_launches.load(); }
+
+// ---- trajectories ------------------------------------------------------------------------------------
+int nb_traj_create(int gpu, const nb_system* sys, int kind, int destroy_device, int math, nb_traj** out) {
+    if (!sys || !out || !sys->q || !sys->v || !sys->m || !sys->is_device) return NB_ERR_ARG;
+    if (sys->n < 1) return NB_ERR_ARG;
+    if (sys->n > NB_MAX_SMALL_N) return NB_ERR_UNSUPPORTED;
+    if (kind < NB_KIND_PLAIN || kind > NB_KIND_Q3 || (math != NB_MATH_FAST && math != NB_MATH_STRICT)) return NB_ERR_ARG;
+    int rc = nb::check_gpu(gpu);
+    if (rc) return rc;
+    nb_traj* t = new nb_traj();
+    t->planet = sys->planet, t->asteroid = sys->asteroid, t->kind = kind, t->destroy_device = destroy_device;
+    t->isdev.assign(sys->is_device, sys->is_device + sys->n);
+    rc = t->b.init(gpu, 1, sys->n, math);
+    if (!rc)
+        rc = t->b.set_system(0, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid, kind, destroy_device, 0);
+    if (rc) {
+        t->b.release();
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return NB_OK;
+}
+
+int nb_traj_run(nb_traj* t, int step_end, nb_events* ev) {
+    if (!t || step_end < 0) return NB_ERR_ARG;
+    int rc = t->b.run(step_end, true);
+    if (rc) return rc;
+    if (ev) *ev = t->b.h_ev[0];
+    return NB_OK;
+}
+
+int nb_traj_state(nb_traj* t, double* q, double* v, double* m, int* step) {
+    if (!t) return NB_ERR_ARG;
+    if (step) *step = t->b.cur_step[0];
+    return t->b.get_state(0, q, v, m);
+}
+
+int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out) {
+    if (!t || !out) return NB_ERR_ARG;
+    const int n = t->b.n;
+    std::vector<double> q(3 * n), v(3 * n), m(n);
+    int rc = t->b.get_state(0, q.data(), v.data(), m.data());
+    if (rc) return rc;
+    nb_traj* f = new nb_traj();
+    f->planet = t->planet, f->asteroid = t->asteroid, f->kind = kind, f->destroy_device = destroy_device;
+    f->isdev = t->isdev;
+    rc = f->b.init(t->b.gpu, 1, n, t->b.math);
+    if (!rc)
+        rc = f->b.set_system(0, q.data(), v.data(), m.data(), f->isdev.data(), f->planet, f->asteroid, kind,
+                             destroy_device, t->b.cur_step[0]);
+    if (rc) {
+        f->b.release();
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return NB_OK;
+}
+
+int nb_traj_destroy(nb_traj* t) {
+    if (!t) return NB_ERR_ARG;
+    t->b.release();
+    delete t;
+    return NB_OK;
+}
+
+// ---- ensembles ---------------------------------------------------------------------------------------
+int nb_ensemble_run(int gpu, int math, int kind, int n_systems, int n, double* q, double* v, const double* m,
+                    const unsigned char* is_device, const int* planet, const int* asteroid, const int* destroy_device,
+                    int step_begin, int step_end, nb_events* ev, double* gpu_seconds) {
+    if (n_systems < 1 || n < 1 || !q || !v || !m || !is_device || step_begin < 0 || step_end < step_begin) return NB_ERR_ARG;
+    if (n > NB_MAX_SMALL_N) return NB_ERR_UNSUPPORTED;
+    if (kind < NB_KIND_PLAIN || kind > NB_KIND_Q3 || (math != NB_MATH_FAST && math != NB_MATH_STRICT)) return NB_ERR_ARG;
+    if (kind == NB_KIND_Q3 && !destroy_device) return NB_ERR_ARG;
+    int rc = nb::check_gpu(gpu);
+    if (rc) return rc;
+    DeviceBatch b;
+    rc = b.init(gpu, n_systems, n, math);
+    for (int s = 0; s < n_systems && !rc; s++)
+        rc = b.set_system(s, q + (size_t)s * 3 * n, v + (size_t)s * 3 * n, m + (size_t)s * n, is_device + (size_t)s * n,
+                          planet ? planet[s] : 0, asteroid ? asteroid[s] : 0, kind,
+                          destroy_device ? destroy_device[s] : -1, step_begin);
+    if (!rc && step_begin > 0) {
+        // resuming: the caller has observed step_begin already
+        for (int s = 0; s < n_systems; s++) b.h_ev[s].steps_done = step_begin;
+        cudaError_t e = cudaMemcpy(b.ev, b.h_ev.data(), n_systems * sizeof(nb_events), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = nb::cuda_fail(e, "cudaMemcpy(ev)", __FILE__, __LINE__);
+    }
+    if (!rc) rc = b.run(step_end, false);
+    for (int s = 0; s < n_systems && !rc; s++) {
+        rc = b.get_state(s, q + (size_t)s * 3 * n, v + (size_t)s * 3 * n, nullptr);
+        if (ev) ev[s] = b.h_ev[s];
+    }
+    if (gpu_seconds) *gpu_seconds = b.gpu_seconds;
+    b.release();
+    return rc;
+}
+
+// ---- the step operator -------------------------------------------------------------------------------
+int nb_large_run_steps_host(int gpu, int math, int n, double* q, double* v, const double* m,
+                            const unsigned char* is_device, int step_begin, int step_end);  // nb_large.cu
+
+int nb_run_steps(int gpu, int math, int n, double* q, double* v, const double* m, const unsigned char* is_device,
+                 int step_begin, int step_end) {
+    if (n < 1 || !q || !v || !m || !is_device || step_begin < 0 || step_end < step_begin) return NB_ERR_ARG;
+    if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
+    int rc = nb::check_gpu(gpu);
+    if (rc) return rc;
+    if (n > NB_MAX_SMALL_N) return nb_large_run_steps_host(gpu, math, n, q, v, m, is_device, step_begin, step_end);
+    DeviceBatch b;
+    rc = b.init(gpu, 1, n, math);
+    if (!rc) rc = b.set_system(0, q, v, m, is_device, 0, 0, NB_KIND_PLAIN, -1, step_begin);
+    if (!rc) rc = b.run(step_end, true);
+    if (!rc) rc = b.get_state(0, q, v, nullptr);
+    b.release();
+    return rc;
+}
+
+// ---- the three queries -------------------------------------------------------------------------------
+// Ensemble scheduler: Q1, Q2 and one Q3 trajectory per device are independent (each Q3 trajectory is
+// re-simulated from step 0 with identical arithmetic, so its prefix equals Q2's: no snapshot
+// transport, no dependency on Q2 — SURVEY §7.2).  Trajectory t goes to gpus[t % n_gpus]; each GPU
+// runs its share as ONE launch from its own host thread; no collective, only scalars come back.
+int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int math, nb_answer* ans) {
+    if (!sys || !ans || !sys->q || !sys->v || !sys->m || !sys->is_device || sys->n < 1 || n_gpus < 1 || n_steps < 0)
+        return NB_ERR_ARG;
+    if (sys->n > NB_MAX_SMALL_N) return NB_ERR_UNSUPPORTED;
+    if (sys->planet < 0 || sys->planet >= sys->n || sys->asteroid < 0 || sys->asteroid >= sys->n) return NB_ERR_ARG;
+    auto t_begin = std::chrono::steady_clock::now();
+    const int n = sys->n;
+    std::vector<int> gl(n_gpus);
+    for (int g = 0; g < n_gpus; g++) {
+        gl[g] = gpus ? gpus[g] : g;
+        int rc = nb::check_gpu(gl[g]);
+        if (rc) return rc;
+    }
+    std::vector<int> devs;
+    for (int i = 0; i < n; i++)
+        if (sys->is_device[i]) devs.push_back(i);
+    const int dc = (int)devs.size();
+    if (dc > NB_MAX_DEVICES) return NB_ERR_UNSUPPORTED;
+
+    struct Job {
+        int kind, destroy;
+    };
+    std::vector<Job> jobs;
+    jobs.push_back({NB_KIND_Q1, -1});
+    jobs.push_back({NB_KIND_Q2, -1});
+    for (int k = 0; k < dc; k++) jobs.push_back({NB_KIND_Q3, devs[k]});
+    const int T = (int)jobs.size();
+    const int G = n_gpus < T ? n_gpus : T;
+    std::vector<nb_events> evs(T);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> details(G);
+    std::vector<double> secs(G, 0.0);
+    std::vector<long long> pairs(G, 0);
+
+    auto worker = [&](int g) {
+        std::vector<int> mine;
+        for (int t = g; t < T; t += G) mine.push_back(t);
+        DeviceBatch b;
+        int rc = b.init(gl[g], (int)mine.size(), n, math);
+        for (size_t s = 0; s < mine.size() && !rc; s++)
+            rc = b.set_system((int)s, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid,
+                              jobs[mine[s]].kind, jobs[mine[s]].destroy, 0);
+        if (!rc) rc = b.run(n_steps, true);
+        if (!rc)
+            for (size_t s = 0; s < mine.size(); s++) evs[mine[s]] = b.h_ev[s];
+        secs[g] = b.gpu_seconds;
+        pairs[g] = b.pairs;
+        b.release();
+        rcs[g] = rc;
+        if (rc) details[g] = nb::g_detail;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(worker, g);
+    worker(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rcs[g]) {
+            nb::set_error_detail(details[g]);
+            return rcs[g];
+        }
+
+    memset(ans, 0, sizeof *ans);
+    ans->min_dist = sqrt(evs[0].min_d2);  // hw5.cu:407
+    ans->argmin_step = evs[0].argmin_step;
+    ans->hit_time_step = evs[1].hit_step;  // -2 when none (nbody.cc:125)
+    ans->gravity_device_id = -1;           // hw5.cu:547-548
+    ans->missile_cost = 0;
+    ans->n_devices = dc;
+    for (int k = 0; k < NB_MAX_DEVICES; k++) {
+        ans->device_index[k] = k < dc ? devs[k] : -1;
+        ans->reach_step[k] = k < dc ? evs[1].reach_step[k] : -2;
+        ans->q3_hit_step[k] = -3;
+        ans->q3_cost[k] = std::numeric_limits<double>::infinity();
+    }
+    if (evs[1].hit_step != -2) {  // hw5.cu:568
+        double best = std::numeric_limits<double>::infinity();
+        for (int k = 0; k < dc; k++) {
+            const nb_events& e = evs[2 + k];
+            ans->q3_hit_step[k] = e.hit_step;
+            ans->q3_cost[k] = e.cost;
+            // hw5.cu:509-517: saved (no hit through n_steps) and cheapest; ties -> lowest device index
+            if (e.hit_step == -2 && e.destroyed_step != -2 && e.cost < best) {
+                best = e.cost;
+                ans->gravity_device_id = devs[k];
+                ans->missile_cost = e.cost;
+            }
+        }
+    }
+    for (int g = 0; g < G; g++) {
+        if (secs[g] > ans->gpu_seconds) ans->gpu_seconds = secs[g];
+        ans->pair_interactions += pairs[g];
+    }
+    ans->n_trajectories = T;
+    ans->n_gpus_used = G;
+    ans->wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    return NB_OK;
+}
+
+}  // extern "C"

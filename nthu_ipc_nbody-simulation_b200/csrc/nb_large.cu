@@ -1,0 +1,317 @@
+// Large-N step (n > 1024, e.g. the 65 536-body synthetic system), optionally body-sharded:
+// this GPU integrates bodies [i_begin, i_begin+i_count) against ALL n bodies.
+//
+// Replaces compute_accelerations_gpu (one thread per ordered pair + 3 FP64 atomics per pair,
+// hw5.cu:159-215) and update_positions_gpu (hw5.cu:231-239).  Arithmetic: nbody.cc:56-88.
+//
+// Data layout in HBM (L2-resident: 2 MiB at n = 65 536):
+//     pos4[n] = {x, y, z, G*m_eff(step)}   one 32-byte record per body, double-buffered by step
+// so that a j-tile is ONE contiguous block: tiles of TJ records are streamed into shared memory
+// with 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP) through a STAGES-deep ring while
+// the FP64 pipe works on the previous tile.  i-bodies live in registers (IPT per thread); every
+// lane of a warp reads the same j record (shared-memory broadcast, 2 LDS.128 per IPT pairs).
+//
+// Grid = (i blocks) x (j splits): each block writes its partial acceleration to
+// apart[split][3][i_count]; nb_large_integrate sums the splits in ascending order (deterministic,
+// no atomics), applies v += a*dt, q += v*dt and emits the next pos4 record with G*m_eff(step+1).
+// The split exists only to cut the work into enough equal pieces to balance 148 SMs.
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "nb_internal.h"
+#include "nb_math.cuh"
+
+namespace nb {
+namespace {
+
+constexpr int TJ = 256;      // bodies per j tile (8 KiB)
+constexpr int STAGES = 3;    // TMA ring depth
+constexpr int LT = 128;      // threads per block
+constexpr int MAX_JSPLIT = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int MATH, int IPT>
+__global__ void __launch_bounds__(LT)
+large_accel_kernel(const double4* __restrict__ pos4, int n, int i_begin, int i_count, int j_per_split,
+                   double* __restrict__ apart) {
+    __shared__ alignas(128) double4 tile[STAGES][TJ];
+    __shared__ alignas(8) uint64_t full[STAGES];
+
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.y * j_per_split;
+    const int j1 = min(n, j0 + j_per_split);
+    const int ntiles = (j1 - j0 + TJ - 1) / TJ;
+
+    double xi[IPT], yi[IPT], zi[IPT], ax[IPT], ay[IPT], az[IPT];
+    int il[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        il[k] = (blockIdx.x * IPT + k) * LT + tid;
+        const double4 p = pos4[i_begin + min(il[k], i_count - 1)];
+        xi[k] = p.x, yi[k] = p.y, zi[k] = p.z;
+        ax[k] = ay[k] = az[k] = 0.0;
+    }
+
+    auto issue = [&](int t) {
+        const int st = t % STAGES;
+        const int jb = j0 + t * TJ;
+        const uint32_t bytes = (uint32_t)(min(TJ, j1 - jb) * sizeof(double4));
+        mbar_expect_tx(&full[st], bytes);
+        tma_load_1d(&tile[st][0], pos4 + jb, bytes, &full[st]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int t = 0; t < STAGES && t < ntiles; t++) issue(t);
+
+    for (int t = 0; t < ntiles; t++) {
+        const int st = t % STAGES;
+        mbar_wait(&full[st], (t / STAGES) & 1);
+        const double4* tj = tile[st];
+        const int cnt = min(TJ, j1 - (j0 + t * TJ));
+        if (cnt == TJ) {
+#pragma unroll 4
+            for (int j = 0; j < TJ; j++) {
+                const double4 b = tj[j];
+#pragma unroll
+                for (int k = 0; k < IPT; k++) pair<MATH>(xi[k], yi[k], zi[k], b.x, b.y, b.z, b.w, ax[k], ay[k], az[k]);
+            }
+        } else {
+            for (int j = 0; j < cnt; j++) {
+                const double4 b = tj[j];
+#pragma unroll
+                for (int k = 0; k < IPT; k++) pair<MATH>(xi[k], yi[k], zi[k], b.x, b.y, b.z, b.w, ax[k], ay[k], az[k]);
+            }
+        }
+        __syncthreads();  // everyone is done with stage st: refill it
+        if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
+    }
+
+    double* out = apart + (size_t)blockIdx.y * 3 * i_count;
+#pragma unroll
+    for (int k = 0; k < IPT; k++)
+        if (il[k] < i_count) {
+            out[il[k]] = ax[k];
+            out[il[k] + i_count] = ay[k];
+            out[il[k] + 2 * i_count] = az[k];
+        }
+}
+
+// sums the j-splits in ascending order, integrates (nbody.cc:77-88), writes the next pos4 record
+__global__ void large_integrate_kernel(const double4* __restrict__ pos4, double4* __restrict__ pos4_out,
+                                       double* __restrict__ vel, const double* __restrict__ m0,
+                                       const unsigned char* __restrict__ is_device, const double* __restrict__ apart,
+                                       int jsplit, int i_begin, int i_count, double fst_next, int strict) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= i_count) return;
+    double a[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double s = apart[(size_t)c * i_count + il];
+        for (int k = 1; k < jsplit; k++) s += apart[((size_t)k * 3 + c) * i_count + il];
+        a[c] = s;
+    }
+    const int i = i_begin + il;
+    const double4 p = pos4[i];
+    double x = p.x, y = p.y, z = p.z;
+    double vx = vel[il], vy = vel[il + i_count], vz = vel[il + 2 * i_count];
+    kick_drift(a[0], vx, x);
+    kick_drift(a[1], vy, y);
+    kick_drift(a[2], vz, z);
+    vel[il] = vx, vel[il + i_count] = vy, vel[il + 2 * i_count] = vz;
+    pos4_out[i] = make_double4(x, y, z, gm_eff(m0[i], is_device[i] != 0, fst_next));
+}
+
+__global__ void large_pack_kernel(int n, const double* __restrict__ q, const double* __restrict__ m0,
+                                  const unsigned char* __restrict__ is_device, double fst_next,
+                                  double4* __restrict__ pos4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos4[i] = make_double4(q[i], q[i + n], q[i + 2 * n], gm_eff(m0[i], is_device[i] != 0, fst_next));
+}
+
+__global__ void large_unpack_kernel(int n, const double4* __restrict__ pos4, double* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 p = pos4[i];
+    q[i] = p.x, q[i + n] = p.y, q[i + 2 * n] = p.z;
+}
+
+int g_ipt = 0;     // 0 = not read yet
+int g_jsplit = -1;  // -1 = not read yet, 0 = heuristic
+void read_env() {
+    if (g_ipt == 0) {
+        const char* e = getenv("NB_LARGE_IPT");
+        int v = e ? atoi(e) : 2;
+        g_ipt = (v == 1 || v == 2 || v == 4) ? v : 2;
+    }
+    if (g_jsplit < 0) {
+        const char* e = getenv("NB_LARGE_JSPLIT");
+        int v = e ? atoi(e) : 0;
+        g_jsplit = (v >= 0 && v <= MAX_JSPLIT) ? v : 0;
+    }
+}
+
+int pick_jsplit(int math, int n, int i_count, int ipt) {
+    if (math == NB_MATH_STRICT) return 1;  // ascending-j sum == the oracle's order
+    if (g_jsplit > 0) return g_jsplit;
+    const int iblocks = (i_count + LT * ipt - 1) / (LT * ipt);
+    int js = 1;
+    // enough equal pieces for ~4 full waves of 148 SMs x 7 resident blocks, >= 2 tiles per piece
+    while (js < MAX_JSPLIT && iblocks * js < 4 * 148 * 7 && n / (js * 2) >= 2 * TJ) js *= 2;
+    return js;
+}
+
+template <int MATH>
+int launch_accel(int ipt, dim3 grid, cudaStream_t st, const double4* pos4, int n, int i_begin, int i_count, int jps,
+                 double* apart) {
+    switch (ipt) {
+        case 1: large_accel_kernel<MATH, 1><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
+        case 2: large_accel_kernel<MATH, 2><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
+        default: large_accel_kernel<MATH, 4><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
+    }
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+}  // namespace
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+long long nb_large_scratch_bytes(int n, int i_count) {
+    (void)n;
+    if (i_count < 1) return 0;
+    return (long long)MAX_JSPLIT * 3 * i_count * (long long)sizeof(double);
+}
+
+int nb_large_pack(int math, int n, const double* q_planar_dev, const double* m0_dev, const unsigned char* is_device_dev,
+                  int step_next, double* pos4_dev, void* stream) {
+    (void)math;
+    if (n < 1 || !q_planar_dev || !m0_dev || !is_device_dev || !pos4_dev || step_next < 0) return NB_ERR_ARG;
+    const double fst = fst_table_host(step_next + 1)[step_next];
+    large_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, q_planar_dev, m0_dev, is_device_dev, fst,
+                                                                         (double4*)pos4_dev);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+int nb_large_unpack(int n, const double* pos4_dev, double* q_planar_dev, void* stream) {
+    if (n < 1 || !pos4_dev || !q_planar_dev) return NB_ERR_ARG;
+    large_unpack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, (const double4*)pos4_dev, q_planar_dev);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+int nb_large_step(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev, double* pos4_out_dev,
+                  double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* scratch_dev,
+                  void* stream) {
+    if (n < 1 || i_begin < 0 || i_count < 1 || i_begin + i_count > n || step < 1) return NB_ERR_ARG;
+    if (!pos4_dev || !pos4_out_dev || !vel_dev || !m0_dev || !is_device_dev || !scratch_dev) return NB_ERR_ARG;
+    if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
+    read_env();
+    const int ipt = g_ipt;
+    const int jsplit = pick_jsplit(math, n, i_count, ipt);
+    int jps = (n + jsplit - 1) / jsplit;
+    jps = ((jps + TJ - 1) / TJ) * TJ;  // whole tiles per split
+    const int nsplit = (n + jps - 1) / jps;
+    dim3 grid((i_count + LT * ipt - 1) / (LT * ipt), nsplit);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = math == NB_MATH_STRICT
+                 ? launch_accel<MATH_STRICT>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
+                                             (double*)scratch_dev)
+                 : launch_accel<MATH_FAST>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
+                                           (double*)scratch_dev);
+    if (rc) return rc;
+    const double fst_next = fst_table_host(step + 2)[step + 1];
+    large_integrate_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, (double4*)pos4_out_dev,
+                                                                  vel_dev, m0_dev, is_device_dev,
+                                                                  (const double*)scratch_dev, nsplit, i_begin, i_count,
+                                                                  fst_next, math == NB_MATH_STRICT);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// host-buffer convenience used by nb_run_steps for n > NB_MAX_SMALL_N (single GPU, all bodies local)
+int nb_large_run_steps_host(int gpu, int math, int n, double* q, double* v, const double* m,
+                            const unsigned char* is_device, int step_begin, int step_end) {
+    NB_CUDA(cudaSetDevice(gpu));
+    cudaStream_t st;
+    NB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    double *dq = nullptr, *dv = nullptr, *dm = nullptr, *pos[2] = {nullptr, nullptr};
+    unsigned char* ddev = nullptr;
+    void* scratch = nullptr;
+    int rc = NB_OK;
+    auto chk = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == NB_OK) rc = cuda_fail(e, what, __FILE__, __LINE__);
+    };
+    chk(cudaMalloc(&dq, 3 * (size_t)n * sizeof(double)), "cudaMalloc q");
+    chk(cudaMalloc(&dv, 3 * (size_t)n * sizeof(double)), "cudaMalloc v");
+    chk(cudaMalloc(&dm, (size_t)n * sizeof(double)), "cudaMalloc m");
+    chk(cudaMalloc(&ddev, (size_t)n), "cudaMalloc is_device");
+    chk(cudaMalloc(&pos[0], 4 * (size_t)n * sizeof(double)), "cudaMalloc pos4");
+    chk(cudaMalloc(&pos[1], 4 * (size_t)n * sizeof(double)), "cudaMalloc pos4");
+    chk(cudaMalloc(&scratch, (size_t)nb_large_scratch_bytes(n, n)), "cudaMalloc scratch");
+    if (rc == NB_OK) {
+        chk(cudaMemcpyAsync(dq, q, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D q");
+        chk(cudaMemcpyAsync(dv, v, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D v");
+        chk(cudaMemcpyAsync(dm, m, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D m");
+        chk(cudaMemcpyAsync(ddev, is_device, (size_t)n, cudaMemcpyHostToDevice, st), "H2D is_device");
+    }
+    if (rc == NB_OK) rc = nb_large_pack(math, n, dq, dm, ddev, step_begin + 1, pos[0], st);
+    int cur = 0;
+    for (int step = step_begin + 1; step <= step_end && rc == NB_OK; step++) {
+        rc = nb_large_step(math, step, n, 0, n, pos[cur], pos[cur ^ 1], dv, dm, ddev, scratch, st);
+        cur ^= 1;
+    }
+    if (rc == NB_OK) rc = nb_large_unpack(n, pos[cur], dq, st);
+    if (rc == NB_OK) {
+        chk(cudaMemcpyAsync(q, dq, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H q");
+        chk(cudaMemcpyAsync(v, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H v");
+        chk(cudaStreamSynchronize(st), "sync");
+    }
+    cudaFree(dq), cudaFree(dv), cudaFree(dm), cudaFree(ddev), cudaFree(pos[0]), cudaFree(pos[1]), cudaFree(scratch);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

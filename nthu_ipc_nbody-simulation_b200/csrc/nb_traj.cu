@@ -1,0 +1,217 @@
+// Persistent single-block trajectory kernel (n <= 1024): one thread block owns one system, keeps
+// every body resident in shared memory and runs all steps AND all observers without returning to
+// the host.  blockIdx.x selects the system, so one launch advances a whole ensemble.
+//
+// Replaces, per step, the reference's compute_accelerations_gpu<<<2D>>> + update_positions_gpu +
+// <<<1,1>>> observer launches (hw5.cu:371-377, 390-397, 496-502) and the host loop around them.
+// Arithmetic: nbody.cc:51-89 (see nb_math.cuh for the two variants).
+//
+// Thread map: thread t -> body i = t / JS, j-slice s = t % JS (JS a power of two <= 32, chosen so
+// that n*JS <= 1024).  Slice s sums j = s, s+JS, ... in ascending order; slices are combined with
+// a warp-shuffle butterfly.  JS == 1 (always used for STRICT) is the reference's ascending-j sum.
+//
+// Shared memory: xy[2][n] (double2) and zg[2][n] (double2 {z, G*m_eff}), double-buffered by step
+// parity so that a step needs two block barriers:
+//     [device G*m_eff(step) -> zg[cur]]  B  [forces from buf cur; owner integrates -> buf cur^1]  B  [observers]
+#include "nb_internal.h"
+#include "nb_math.cuh"
+
+namespace nb {
+
+namespace {
+
+struct Observed {
+    double min_d2;
+    int argmin_step;
+    int hit_step;
+    int destroyed_step;
+    double cost;
+};
+
+template <int MATH, int JS>
+__global__ void __launch_bounds__(1024, 1)
+traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst) {
+    extern __shared__ double2 smem2[];
+    const TrajDesc d = descs[blockIdx.x];
+    const int n = d.n;
+    double2* xy = smem2;          // [2][n]
+    double2* zg = smem2 + 2 * n;  // [2][n]
+    const int tid = threadIdx.x;
+    const int i_raw = tid / JS;
+    const int s = tid % JS;
+    const bool active = i_raw < n;
+    const int i = active ? i_raw : n - 1;
+    const bool owner = active && (s == 0);
+
+    // owner state
+    double vx = 0, vy = 0, vz = 0;
+    if (owner) {
+        double x = d.q[i], y = d.q[i + n], z = d.q[i + 2 * n];
+        vx = d.v[i];
+        vy = d.v[i + n];
+        vz = d.v[i + 2 * n];
+        double gm = d.is_device[i] ? 0.0 : gm_eff(d.m[i], false, 0.0);
+        xy[i] = make_double2(x, y);
+        xy[n + i] = make_double2(x, y);
+        zg[i] = make_double2(z, gm);
+        zg[n + i] = make_double2(z, gm);
+    }
+    // device bookkeeping: thread k < n_dev looks after device k
+    int my_dev = -1, my_reach = -2;
+    double my_m0 = 0.0;
+    if (tid < d.n_dev) {
+        my_dev = d.dev_index[tid];
+        my_m0 = d.m[my_dev];
+        my_reach = d.ev->reach_step[tid];
+    }
+    Observed ob;
+    ob.min_d2 = d.ev->min_d2;
+    ob.argmin_step = d.ev->argmin_step;
+    ob.hit_step = d.ev->hit_step;
+    ob.destroyed_step = d.ev->destroyed_step;
+    ob.cost = d.ev->cost;
+    const int kind = d.kind;
+    const int P = d.planet, A = d.asteroid, DD = d.destroy_device;
+    const bool q3_armed = (kind == NB_KIND_Q3) && DD >= 0 && DD < n && d.m[DD] != 0.0;  // hw5.cu:299
+    __syncthreads();
+
+    int cur = 0;
+    int step = d.step_begin;
+    bool stop = (kind >= NB_KIND_Q2) && ob.hit_step != -2;
+
+    // Observers of one step, on buffer `b` (uniform across the block except the per-device reach test).
+    auto observe = [&](int st, int b) {
+        const double2 pxy = xy[b * n + P], pzg = zg[b * n + P];
+        const double2 axy = xy[b * n + A], azg = zg[b * n + A];
+        const double d2 = dist2_rn(pxy.x, pxy.y, pzg.x, axy.x, axy.y, azg.x);
+        if (d2 < ob.min_d2) {  // hw5.cu:245-247
+            ob.min_d2 = d2;
+            ob.argmin_step = st;
+        }
+        if (kind == NB_KIND_Q2 && my_dev >= 0 && my_reach == -2) {  // hw5.cu:265-287 (before the hit test, :396-397)
+            const double2 dxy = xy[b * n + my_dev], dzg = zg[b * n + my_dev];
+            const double md = __dmul_rn(MISSILE_STEP, (double)st);
+            if (dist2_rn(pxy.x, pxy.y, pzg.x, dxy.x, dxy.y, dzg.x) < __dmul_rn(md, md)) my_reach = st;
+        }
+        if (kind >= NB_KIND_Q2) {
+            if (d2 < PLANET_RADIUS2) {  // nbody.cc:134, hw5.cu:295-298
+                ob.hit_step = st;
+                stop = true;
+            } else if (q3_armed && ob.destroyed_step == -2) {  // hw5.cu:299-307
+                const double2 dxy = xy[b * n + DD], dzg = zg[b * n + DD];
+                const double md = __dmul_rn(MISSILE_STEP, (double)st);
+                if (dist2_rn(pxy.x, pxy.y, pzg.x, dxy.x, dxy.y, dzg.x) < __dmul_rn(md, md)) {
+                    ob.destroyed_step = st;
+                    ob.cost = __dadd_rn(1e5, __dmul_rn(1e3, __dmul_rn((double)(st + 1), DT)));
+                }
+            }
+        }
+    };
+
+    if (d.ev->steps_done < step && !stop) observe(step, cur);
+
+    while (!stop && step < d.step_end) {
+        ++step;
+        // (1) G*m_eff of the devices for this step (nbody.cc:61-64); a destroyed device has mass 0
+        if (my_dev >= 0) {
+            const bool gone = (kind == NB_KIND_Q3) && my_dev == DD && ob.destroyed_step != -2;
+            zg[cur * n + my_dev].y = gm_eff(gone ? 0.0 : my_m0, true, fst[step]);
+        }
+        __syncthreads();
+        // (2) forces on body i from slice s of the bodies (nbody.cc:56-74)
+        const double2* cxy = xy + cur * n;
+        const double2* czg = zg + cur * n;
+        const double2 ixy = cxy[i], izg = czg[i];
+        const double xi = ixy.x, yi = ixy.y, zi = izg.x;
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        if (JS == 1) {
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const double2 jxy = cxy[j], jzg = czg[j];
+                pair<MATH>(xi, yi, zi, jxy.x, jxy.y, jzg.x, jzg.y, ax, ay, az);
+            }
+        } else {
+#pragma unroll 2
+            for (int j = s; j < n; j += JS) {
+                const double2 jxy = cxy[j], jzg = czg[j];
+                pair<MATH>(xi, yi, zi, jxy.x, jxy.y, jzg.x, jzg.y, ax, ay, az);
+            }
+#pragma unroll
+            for (int o = JS / 2; o > 0; o >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
+                az += __shfl_xor_sync(0xffffffffu, az, o);
+            }
+        }
+        // (3) v += a*dt; q += v*dt (nbody.cc:77-88) into the other buffer
+        if (owner) {
+            double x = xi, y = yi, z = zi;
+            kick_drift(ax, vx, x);
+            kick_drift(ay, vy, y);
+            kick_drift(az, vz, z);
+            xy[(cur ^ 1) * n + i] = make_double2(x, y);
+            zg[(cur ^ 1) * n + i].x = z;
+        }
+        __syncthreads();
+        cur ^= 1;
+        observe(step, cur);
+    }
+
+    // write back
+    if (owner) {
+        const double2 fxy = xy[cur * n + i], fzg = zg[cur * n + i];
+        d.q[i] = fxy.x;
+        d.q[i + n] = fxy.y;
+        d.q[i + 2 * n] = fzg.x;
+        d.v[i] = vx;
+        d.v[i + n] = vy;
+        d.v[i + 2 * n] = vz;
+    }
+    if (tid < d.n_dev) d.ev->reach_step[tid] = my_reach;
+    if (tid == 0) {
+        d.ev->min_d2 = ob.min_d2;
+        d.ev->argmin_step = ob.argmin_step;
+        d.ev->hit_step = ob.hit_step;
+        d.ev->destroyed_step = ob.destroyed_step;
+        d.ev->cost = ob.cost;
+        d.ev->steps_done = step;
+        d.ev->n_reach = d.n_dev;
+        if (kind == NB_KIND_Q3 && ob.destroyed_step != -2) d.m[DD] = 0.0;  // hw5.cu:306
+    }
+}
+
+template <int MATH, int JS>
+int launch(int n, int n_traj, const TrajDesc* descs, const double* fst, cudaStream_t stream) {
+    const size_t smem = (size_t)4 * n * sizeof(double2);
+    NB_CUDA(cudaFuncSetAttribute(traj_kernel<MATH, JS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = ((n * JS + 31) / 32) * 32;
+    traj_kernel<MATH, JS><<<n_traj, threads, smem, stream>>>(descs, fst);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+}  // namespace
+
+int traj_js_for(int math, int n) {
+    if (math == NB_MATH_STRICT) return 1;
+    int js = 1;
+    while (js < 32 && n * js * 2 <= 1024) js *= 2;
+    return js;
+}
+
+int launch_traj_batch(int math, int n, int n_traj, const TrajDesc* descs, const double* fst, cudaStream_t stream) {
+    if (n < 1 || n > NB_MAX_SMALL_N || n_traj < 1) return NB_ERR_ARG;
+    if (math == NB_MATH_STRICT) return launch<MATH_STRICT, 1>(n, n_traj, descs, fst, stream);
+    if (math != NB_MATH_FAST) return NB_ERR_ARG;
+    switch (traj_js_for(math, n)) {
+        case 1: return launch<MATH_FAST, 1>(n, n_traj, descs, fst, stream);
+        case 2: return launch<MATH_FAST, 2>(n, n_traj, descs, fst, stream);
+        case 4: return launch<MATH_FAST, 4>(n, n_traj, descs, fst, stream);
+        case 8: return launch<MATH_FAST, 8>(n, n_traj, descs, fst, stream);
+        case 16: return launch<MATH_FAST, 16>(n, n_traj, descs, fst, stream);
+        default: return launch<MATH_FAST, 32>(n, n_traj, descs, fst, stream);
+    }
+}
+
+}  // namespace nb

@@ -1,0 +1,295 @@
+"""GPU: the CUDA path through the C ABI against the CPU oracle, the goldens and the oracle KATs.
+
+Bars (BASELINE.json north_star): hit step, device id, missile cost bit-exact; min distance within
+1e-6 relative (MIN_DIST_RTOL below).  Stronger checks where the arithmetic allows: the STRICT kernel
+is bit-identical to the oracle's sqrt3 mode on the full state."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from conftest import CASES, GOLDEN, case_path, golden_lines
+
+pytestmark = pytest.mark.gpu
+MIN_DIST_RTOL = 1e-6  # tolerance the north star states for output line 1
+
+
+def ulps(a, b):
+    return np.abs(a - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def kats():
+    return json.load(open(os.path.join(GOLDEN, "oracle_kats.json")))
+
+
+# ---- state-level parity --------------------------------------------------------------------------
+@pytest.mark.parametrize("case,steps", [("b20", 3000), ("b100", 1000), ("b200", 400), ("b512", 60), ("b1024", 20)])
+def test_strict_kernel_state_is_bit_identical_to_oracle(nb, oracle, case, steps):
+    s = nb.read_input(case_path(case))
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, steps, s.n, q, v, s.m, s.is_device, math=nb.MATH_STRICT)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 0, steps)
+    assert np.array_equal(q, qo)
+    assert np.array_equal(v, vo)
+
+
+@pytest.mark.parametrize("case,steps", [("b20", 3000), ("b60", 1000), ("b100", 1000), ("b200", 400), ("b512", 60),
+                                        ("b1024", 20)])
+def test_fast_kernel_state_matches_oracle(nb, oracle, case, steps):
+    """Fast math (rsqrt seed + correction, FMA, lane-split sums): positions equal to the last bit or
+    two, velocities to 1e-12 relative — SURVEY App. B explains why the rounded state absorbs it."""
+    s = nb.read_input(case_path(case))
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, steps, s.n, q, v, s.m, s.is_device, math=nb.MATH_FAST)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_STRICT, s.n, qo, vo, s.m, s.is_device, 0, steps)
+    assert ulps(q, qo).max() <= 2
+    assert np.allclose(v, vo, rtol=1e-12, atol=0)
+
+
+def test_run_step_is_the_reference_operator(nb, oracle):
+    """run_step(step, ...) one step at a time == many steps in one call (step index drives the device mass)."""
+    s = nb.read_input(case_path("b30"))
+    q, v = s.q.copy(), s.v.copy()
+    for step in range(1, 6):
+        nb.run_step(step, s.n, q, v, s.m, s.is_device, math=nb.MATH_STRICT)
+    q2, v2 = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 5, s.n, q2, v2, s.m, s.is_device, math=nb.MATH_STRICT)
+    assert np.array_equal(q, q2) and np.array_equal(v, v2)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 0, 5)
+    assert np.array_equal(q, qo) and np.array_equal(v, vo)
+    # a later step index gives a different device mass, hence a different state
+    q3, v3 = s.q.copy(), s.v.copy()
+    nb.run_steps(100, 105, s.n, q3, v3, s.m, s.is_device, math=nb.MATH_STRICT)
+    assert not np.array_equal(v3, v2)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 100, 105)
+    assert np.array_equal(q3, qo) and np.array_equal(v3, vo)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 33, 1000, 1024])
+def test_edge_sizes_small_path(nb, oracle, n):
+    """Ragged / minimal systems through the persistent kernel (n == 1 has no pair at all)."""
+    s = nb.synthetic_system(max(n, 6), seed=n)
+    q, v, m, dev = (s.q.reshape(3, -1)[:, :n].copy().reshape(-1), s.v.reshape(3, -1)[:, :n].copy().reshape(-1),
+                    s.m[:n].copy(), s.is_device[:n].copy())
+    if n >= 3:
+        dev[-1] = 1
+    qo, vo = q.copy(), v.copy()
+    nb.run_steps(0, 7, n, q, v, m, dev, math=nb.MATH_STRICT)
+    oracle.run_steps(oracle.MODE_SQRT3, n, qo, vo, m, dev, 0, 7)
+    assert np.array_equal(q, qo) and np.array_equal(v, vo)
+
+
+# ---- the three queries against the goldens ---------------------------------------------------------
+@pytest.mark.parametrize("case", CASES)
+def test_solve_matches_golden(nb, case, kats):
+    s = nb.read_input(case_path(case))
+    g = golden_lines(case)
+    ans = nb.solve(s, gpus=[0])
+    assert ans.hit_time_step == g["hit_time_step"]            # bit-exact
+    assert ans.gravity_device_id == g["gravity_device_id"]    # bit-exact
+    assert ans.missile_cost == g["missile_cost"]              # bit-exact
+    assert abs(ans.min_dist - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+    if case in kats:  # intermediate known answers of the oracle
+        k = kats[case]
+        assert ans.argmin_step == k["argmin_step"]
+        for j, d in enumerate(k["devices"]):
+            assert ans.device_index[j] == d["index"]
+            assert ans.reach_step[j] == d["reach_step"]
+            assert ans.q3_hit_step[j] == d["q3_hit_step"]
+
+
+def test_solve_output_file_is_byte_identical_for_small_goldens(nb, tmp_path):
+    """Stronger than the bar: on these inputs even line 1 comes out to the last digit."""
+    for case in ("b20", "b30", "b50"):
+        out = tmp_path / (case + ".out")
+        nb.hw5_main(case_path(case), str(out), 1)
+        assert out.read_text() == golden_lines(case)["text"]
+
+
+def test_hw5_cli_binary(nb, tmp_path):
+    out = tmp_path / "b40.out"
+    r = subprocess.run([nb.HW5_PATH, case_path("b40"), str(out)], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    g = golden_lines("b40")
+    a, b, c = out.read_text().split("\n")[:3]
+    assert b == str(g["hit_time_step"]) and c == g["text"].split("\n")[2]
+    assert abs(float(a) - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+
+
+def test_solve_strict_math_matches_golden_b20(nb):
+    s = nb.read_input(case_path("b20"))
+    g = golden_lines("b20")
+    ans = nb.solve(s, gpus=[0], math=nb.MATH_STRICT)
+    assert nb.format_output(ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == g["text"]
+
+
+def test_no_hit_defaults(nb, oracle):
+    """No collision inside the horizon: -2 and '-1 0' (hw5.cu:545-548,568); no golden pins this path."""
+    s = nb.read_input(case_path("b20"))
+    ans = nb.solve(s, gpus=[0], n_steps=1000)
+    ref = oracle.solve(oracle.MODE_STRICT, s, n_steps=1000)
+    assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (-2, -1, 0.0)
+    assert ans.min_dist == ref.min_dist and ans.argmin_step == ref.argmin_step
+
+
+# ---- trajectories / events -------------------------------------------------------------------------
+def test_trajectory_events_match_oracle(nb, oracle):
+    s = nb.read_input(case_path("b30"))
+    for kind, okind, dd in ((nb.KIND_Q1, oracle.KIND_Q1, -1), (nb.KIND_Q2, oracle.KIND_Q2, -1),
+                            (nb.KIND_Q3, oracle.KIND_Q3, 28), (nb.KIND_Q3, oracle.KIND_Q3, 29)):
+        t = nb.Trajectory(s, kind, dd)
+        ev = t.run(nb.N_STEPS)
+        oev, qo, vo = oracle.trajectory(oracle.MODE_STRICT, okind, s, dd)
+        assert ev.hit_step == oev.hit_step and ev.destroyed_step == oev.destroyed_step
+        assert ev.argmin_step == oev.argmin_step and ev.steps_done == oev.steps_done
+        assert ev.cost == oev.cost
+        assert abs(ev.min_d2 - oev.min_d2) <= 2e-6 * oev.min_d2
+        assert list(ev.reach_step[:ev.n_reach]) == list(oev.reach_step[:oev.n_reach])
+        q, v, m, step = t.state()
+        assert step == oev.steps_done
+        assert ulps(q, qo).max() <= 4
+        if kind == nb.KIND_Q3:
+            assert m[dd] == 0.0  # hw5.cu:306
+        t.close()
+
+
+def test_trajectory_resume_and_fork(nb):
+    """Stopping and resuming a persistent trajectory changes nothing; a fork at the missile-reach
+    step (hw5.cu:275-284 snapshot -> :482-483 restore) equals the trajectory simulated from step 0."""
+    s = nb.read_input(case_path("b50"))
+    a = nb.Trajectory(s, nb.KIND_Q2)
+    ea = a.run(nb.N_STEPS)
+    b = nb.Trajectory(s, nb.KIND_Q2)
+    for end in (1, 2, 1000, 87218, 87219, nb.N_STEPS):
+        eb = b.run(end)
+    assert eb.as_dict() == ea.as_dict()
+    assert all(np.array_equal(x, y) for x, y in zip(a.state()[:2], b.state()[:2]))
+    r = ea.reach_step[0]  # device 48
+    c = nb.Trajectory(s, nb.KIND_Q2)
+    c.run(r)
+    f = c.fork(nb.KIND_Q3, 48)
+    ef = f.run(nb.N_STEPS)
+    d = nb.Trajectory(s, nb.KIND_Q3, 48)
+    ed = d.run(nb.N_STEPS)
+    assert (ef.hit_step, ef.destroyed_step, ef.cost) == (ed.hit_step, ed.destroyed_step, ed.cost) == (-2, r, 5.23324e9)
+    assert all(np.array_equal(x, y) for x, y in zip(f.state()[:2], d.state()[:2]))
+    for t in (a, b, c, d, f):
+        t.close()
+
+
+def test_error_codes_on_gpu(nb):
+    s = nb.read_input(case_path("b20"))
+    with pytest.raises(nb.NbodyError) as e:
+        nb.Trajectory(s, nb.KIND_Q1, gpu=99)
+    assert e.value.code == nb.NB_ERR_NO_GPU
+    big = nb.synthetic_system(2048)
+    with pytest.raises(nb.NbodyError) as e:
+        nb.Trajectory(big, nb.KIND_Q1)
+    assert e.value.code == nb.NB_ERR_UNSUPPORTED
+    with pytest.raises(nb.NbodyError) as e:
+        nb.Trajectory(s, nb.KIND_Q3, destroy_device=500)
+    assert e.value.code == nb.NB_ERR_ARG
+
+
+# ---- ensembles ---------------------------------------------------------------------------------------
+def test_ensemble_members_match_individual_runs(nb, oracle):
+    """SURVEY §8d config C4 in miniature: member k = the golden system with velocities scaled by (1 + 1e-9 k)."""
+    s = nb.read_input(case_path("b100"))
+    S, steps = 12, 300
+    q = np.tile(s.q, (S, 1))
+    v = np.stack([s.v * (1 + 1e-9 * k) for k in range(S)])
+    m = np.tile(s.m, (S, 1))
+    dev = np.tile(s.is_device, (S, 1))
+    q_in, v_in = q.copy(), v.copy()
+    ev, secs = nb.ensemble_run(q, v, m, dev, [s.planet] * S, [s.asteroid] * S, kind=nb.KIND_Q2, step_end=steps,
+                               math=nb.MATH_STRICT)
+    assert secs > 0
+    for k in (0, 5, S - 1):
+        qo, vo = q_in[k].copy(), v_in[k].copy()
+        oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 0, steps)
+        assert np.array_equal(q[k], qo) and np.array_equal(v[k], vo)
+        assert ev[k].steps_done == steps and ev[k].hit_step == -2
+    assert not np.array_equal(q[1], q[2])
+
+
+# ---- large-N path ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1025, 3000, 4096])
+def test_large_path_strict_bitwise(nb, oracle, n):
+    """n > 1024 goes through the tiled TMA kernel; STRICT sums j ascending in one split -> bit-identical."""
+    s = nb.synthetic_system(n, seed=3)
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 3, n, q, v, s.m, s.is_device, math=nb.MATH_STRICT)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, n, qo, vo, s.m, s.is_device, 0, 3)
+    assert np.array_equal(q, qo) and np.array_equal(v, vo)
+
+
+def test_large_path_fast_accelerations(nb, oracle):
+    """SURVEY §8d C5 parity: after one step from rest v = a*dt; every component within 1e-12 of the
+    body's largest acceleration component; after 10 steps q within 1e-12*max|v|*dt, v within 1e-12."""
+    n = 8192
+    s = nb.synthetic_system(n, seed=42)
+    rest = s.copy()
+    rest.v[:] = 0.0
+    q, v = rest.q.copy(), rest.v.copy()
+    nb.run_steps(0, 1, n, q, v, rest.m, rest.is_device)
+    qo, vo = rest.q.copy(), rest.v.copy()
+    oracle.run_steps(oracle.MODE_STRICT, n, qo, vo, rest.m, rest.is_device, 0, 1)
+    scale = np.abs(vo.reshape(3, -1)).max(axis=0)
+    assert (np.abs(v - vo).reshape(3, -1) / scale).max() < 1e-12
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 10, n, q, v, s.m, s.is_device)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, n, qo, vo, s.m, s.is_device, 0, 10)
+    assert np.abs(q - qo).max() <= max(1e-12 * np.abs(vo).max() * 60.0, 2 * np.spacing(np.abs(qo)).max())
+    assert np.allclose(v, vo, rtol=1e-12, atol=0)
+
+
+def test_sharded_single_rank_matches_host_api(nb):
+    """The torch-plumbed device-pointer path (nb_large_pack / nb_large_step) == nb_run_steps."""
+    import torch
+
+    n = 4096
+    s = nb.synthetic_system(n, seed=11)
+    sh = nb.ShardedSystem(s, rank=0, world=1, device="cuda:0")
+    sh.advance(5)
+    torch.cuda.synchronize()
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 5, n, q, v, s.m, s.is_device)
+    assert np.array_equal(sh.positions(), q) and np.array_equal(sh.velocities(), v)
+
+
+def test_two_shards_on_one_gpu_equal_one_shard(nb):
+    """Body sharding is exact: integrating [0, n/2) and [n/2, n) separately against all bodies and
+    exchanging pos4 rows gives the unsharded result bit for bit (the all-gather is emulated by a copy)."""
+    import torch
+
+    n = 2048
+    s = nb.synthetic_system(n, seed=5)
+    whole = nb.ShardedSystem(s, rank=0, world=1, device="cuda:0")
+    parts = [nb.ShardedSystem(s, rank=r, world=2, device="cuda:0") for r in range(2)]
+    for p in parts:
+        p.world = 1  # no process group here: the exchange is done by hand below
+    for _ in range(4):
+        whole.advance(1)
+        for p in parts:
+            p.advance(1)
+        a, b = parts
+        h = n // 2
+        a.pos4[a.cur][h:] = b.pos4[b.cur][h:]
+        b.pos4[b.cur][:h] = a.pos4[a.cur][:h]
+    torch.cuda.synchronize()
+    assert torch.equal(whole.pos4[whole.cur], parts[0].pos4[parts[0].cur])
+    assert torch.equal(whole.pos4[whole.cur], parts[1].pos4[parts[1].cur])
+    assert torch.equal(whole.vel[:, : n // 2], parts[0].vel) and torch.equal(whole.vel[:, n // 2:], parts[1].vel)
+
+
+def test_fp64_peak_is_plausible(nb):
+    tf = nb.fp64_peak(0)
+    assert 15.0 < tf < 45.0, tf

@@ -139,6 +139,15 @@ int nb_ensemble_run(int gpu, int math, int kind, int n_systems, int n, double* q
  * gpus == NULL means ordinals 0..n_gpus-1.
  */
 int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int math, nb_answer* ans);
+/* The same, split for one-process-per-GPU launches (torchrun): trajectory t (0 = Q1, 1 = Q2,
+ * 2+k = Q3 with device k destroyed) belongs to part t % n_parts.  nb_solve_partial runs this
+ * part's trajectories on `gpu` and fills evs[t] for them (evs has nb_solve_trajectory_count()
+ * entries); after the parts' entries have been gathered, nb_solve_combine applies the selection
+ * rule of hw5.cu:509-517, 568-602. */
+int nb_solve_trajectory_count(const nb_system* sys, int* count);
+int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n_steps, int math,
+                     nb_events* evs, double* gpu_seconds, long long* pair_interactions);
+int nb_solve_combine(const nb_system* sys, const nb_events* evs, nb_answer* ans);
 
 /* ---- file formats (nbody.cc:22-49, hw5.cu:86-141) ------------------------------------------- */
 int nb_read_header(const char* path, int* n, int* planet, int* asteroid);
@@ -170,6 +179,14 @@ int nb_large_step(int math, int step, int n, int i_begin, int i_count, const dou
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */
 int nb_fp64_peak(int gpu, double* tflops, double* seconds);
+/* the same with register-operand DFMAs: variant 1 = three distinct register pairs per DFMA,
+ * variant 2 = one multiplicand shared by consecutive DFMAs (operand-reuse pattern) */
+int nb_fp64_peak_variant(int gpu, int variant, double* tflops);
+/* When enabled, nb_large_step brackets its acceleration kernel with CUDA events on the caller's
+ * stream (calling thread only) and accumulates the durations; nb_profile_read synchronises and
+ * returns the total milliseconds and the number of launches since the last enable. */
+int nb_profile_enable(int on);
+int nb_profile_read(double* accel_ms, long long* accel_launches);
 
 #ifdef __cplusplus
 }

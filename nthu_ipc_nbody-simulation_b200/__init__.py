@@ -66,8 +66,9 @@ class NbAnswer(C.Structure):
 ABI_SYMBOLS = [
     "nb_version", "nb_strerror", "nb_last_error_detail", "nb_device_count", "nb_kernel_launches",
     "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_destroy",
-    "nb_ensemble_run", "nb_solve", "nb_read_header", "nb_read_input", "nb_write_output", "nb_hw5_main",
-    "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_fp64_peak",
+    "nb_ensemble_run", "nb_solve", "nb_solve_trajectory_count", "nb_solve_partial", "nb_solve_combine",
+    "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_hw5_main",
+    "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_fp64_peak", "nb_fp64_peak_variant",
 ]
 
 _lib_handle = None
@@ -100,6 +101,12 @@ def lib():
     L.nb_ensemble_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _up, _ip, _ip, _ip,
                                   C.c_int, C.c_int, C.POINTER(NbEvents), _dp]
     L.nb_solve.argtypes = [C.POINTER(NbSystem), _ip, C.c_int, C.c_int, C.c_int, C.POINTER(NbAnswer)]
+    L.nb_solve_trajectory_count.argtypes = [C.POINTER(NbSystem), _ip]
+    L.nb_solve_partial.argtypes = [C.POINTER(NbSystem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(NbEvents), _dp, C.POINTER(C.c_longlong)]
+    L.nb_solve_combine.argtypes = [C.POINTER(NbSystem), C.POINTER(NbEvents), C.POINTER(NbAnswer)]
+    L.nb_profile_enable.argtypes = [C.c_int]
+    L.nb_profile_read.argtypes = [_dp, C.POINTER(C.c_longlong)]
     L.nb_read_header.argtypes = [C.c_char_p, _ip, _ip, _ip]
     L.nb_read_input.argtypes = [C.c_char_p, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _up]
     L.nb_write_output.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double]
@@ -111,6 +118,7 @@ def lib():
     L.nb_large_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nb_fp64_peak.argtypes = [C.c_int, _dp, _dp]
+    L.nb_fp64_peak_variant.argtypes = [C.c_int, C.c_int, _dp]
     _lib_handle = L
     return L
 
@@ -272,6 +280,58 @@ def solve(system, gpus=None, n_steps=N_STEPS, math=MATH_FAST):
     return ans
 
 
+def solve_partial(system, gpu, part, n_parts, n_steps=N_STEPS, math=MATH_FAST):
+    """This part's share of the trajectories (t % n_parts == part) on `gpu`.
+    Returns (events array with this part's entries filled, gpu_seconds, pair_interactions)."""
+    cs = system._c()
+    cnt = C.c_int()
+    _check(lib().nb_solve_trajectory_count(C.byref(cs), C.byref(cnt)))
+    evs = (NbEvents * cnt.value)()
+    secs, pairs = C.c_double(), C.c_longlong()
+    _check(lib().nb_solve_partial(C.byref(cs), gpu, part, n_parts, n_steps, math, evs, C.byref(secs), C.byref(pairs)))
+    return evs, secs.value, pairs.value
+
+
+def solve_combine(system, evs):
+    cs = system._c()
+    ans = NbAnswer()
+    _check(lib().nb_solve_combine(C.byref(cs), evs, C.byref(ans)))
+    return ans
+
+
+def solve_distributed(system, rank, world, gpu, n_steps=N_STEPS, math=MATH_FAST, group=None):
+    """One process per GPU (torchrun): every rank simulates its share of the trajectories, the
+    nb_events structs (a few hundred bytes each) are gathered with torch.distributed — the path has
+    no data-path collective — and every rank applies the selection rule.  Returns (answer,
+    max gpu_seconds over ranks, total pair interactions)."""
+    evs, secs, pairs = solve_partial(system, gpu, rank, world, n_steps, math)
+    if world > 1:
+        import torch.distributed as dist
+
+        blobs = [None] * world
+        dist.all_gather_object(blobs, (bytes(evs), secs, pairs), group=group)
+        T = len(evs)
+        merged = (NbEvents * T)()
+        for r, (b, s_r, p_r) in enumerate(blobs):
+            part = (NbEvents * T).from_buffer_copy(b)
+            for t in range(r, T, world):
+                merged[t] = part[t]
+        evs = merged
+        secs = max(b[1] for b in blobs)
+        pairs = sum(b[2] for b in blobs)
+    return solve_combine(system, evs), secs, pairs
+
+
+def profile_enable(on=True):
+    _check(lib().nb_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    ms, cnt = C.c_double(), C.c_longlong()
+    _check(lib().nb_profile_read(C.byref(ms), C.byref(cnt)))
+    return ms.value, cnt.value
+
+
 def format_output(min_dist, hit_time_step, gravity_device_id, missile_cost):
     return "%.16e\n%d\n%d %.16e\n" % (min_dist, hit_time_step, gravity_device_id, missile_cost)
 
@@ -281,9 +341,12 @@ def hw5_main(input_path, output_path, n_gpus=0):
     _check(lib().nb_hw5_main(os.fsencode(input_path), os.fsencode(output_path), n_gpus))
 
 
-def fp64_peak(gpu=0):
+def fp64_peak(gpu=0, variant=0):
     t, s = C.c_double(), C.c_double()
-    _check(lib().nb_fp64_peak(gpu, C.byref(t), C.byref(s)))
+    if variant:
+        _check(lib().nb_fp64_peak_variant(gpu, variant, C.byref(t)))
+    else:
+        _check(lib().nb_fp64_peak(gpu, C.byref(t), C.byref(s)))
     return t.value
 
 

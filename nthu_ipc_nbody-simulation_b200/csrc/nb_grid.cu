@@ -1,11 +1,385 @@
-// Whole-GPU cooperative persistent trajectory kernel (placeholder until the first GPU measurement
-// of the single-block kernel is in): reports "unsupported" so that DeviceBatch::run uses nb_traj.cu.
+// Whole-GPU cooperative persistent trajectory kernel: ONE system (or up to 4 systems of the same n
+// in lock step) spread over up to 128 SMs, all steps and observers in one launch.  This is the
+// low-step-latency path for the b512 / b1024 queries: a single block needs ~133 us per b1024 step
+// (nb_traj.cu), the FP64 floor over 128 SMs is ~1.05 us.
+//
+// Replaces the host-driven per-step launch sequence of the reference (hw5.cu:368-404, 387-403,
+// 489-508: 3-4 kernel launches per step, 600 000-800 000 per trajectory).  Arithmetic: nbody.cc:51-89.
+//
+// Decomposition: block c owns bodies [8c, 8c+8); warp w of the block owns bodies 8c+2w, 8c+2w+1 and
+// its 32 lanes split the j range (j = lane, lane+32, ...), two i-bodies per j record so that the
+// shared-memory traffic stays at half the FP64 issue rate.  A 5-round xor butterfly combines the
+// lanes; lanes 0-5 each integrate one (body, component) and publish the new coordinate.
+//
+// Exchange (the step's only grid-wide dependency): every block publishes its 8 new positions
+// (192 B, body-major x,y,z) into a double-buffered global record array (L2 resident) and each warp
+// releases a step-counter flag; in every block warp w acquires the flags of producer blocks
+// 32w..32w+31 (one per lane) and then copies their records, coalesced 16 B per lane, into the
+// block's shared memory (raw records, double-buffered by step parity; lanes at consecutive j read
+// them at a 24 B stride, which is bank-conflict free for 8 B accesses).  One __syncthreads later
+// every block holds all positions of the new step.  No grid-wide barrier object, no atomics: 2 block barriers
+// and one release/acquire hop per step.  Spins are bounded (clock64) and raise `status`.
+//
+// Co-residency of all blocks is guaranteed by the cooperative launch (grid <= SM count, 1 block/SM).
+#include <cstdint>
+#include <cstdlib>
+
 #include "nb_internal.h"
+#include "nb_math.cuh"
 
 namespace nb {
-bool grid_traj_supported(int, int, int) { return false; }
-size_t grid_traj_workspace_bytes(int, int) { return 0; }
-int launch_grid_traj(int, int, int, const TrajDesc*, const double*, int, void*, size_t, cudaStream_t) {
-    return NB_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int GB = 8;         // bodies per block
+constexpr int GT = 128;       // threads per block (4 warps x 2 bodies)
+constexpr int REC = GB * 3;   // doubles per block record
+constexpr int MAX_T = 4;      // trajectories per launch (shared memory: 56 B x npad each)
+constexpr long long SPIN_LIMIT = 4000000000LL;  // ~2 s of SM clocks
+
+__device__ __forceinline__ uint4 ld_acquire_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 ld_strong_d2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_strong_d(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+struct TState {  // per trajectory, per thread (registers after unrolling)
+    // uniform
+    int n_dev, kind, P, A, DD, step, step_end;
+    bool q3_armed, active;
+    double min_d2, cost;
+    int argmin_step, hit_step, destroyed_step;
+    // device bookkeeping (thread k < n_dev)
+    int my_dev, my_reach;
+    double my_m0;
+    // integrator lanes (lane < 6)
+    double v, q;
+    double fst_next;  // |sin| of the next step, prefetched (the acquire polls invalidate L1 every step)
+    int cur;
+};
+
+template <int MATH, int T>
+__global__ void __launch_bounds__(GT, 1)
+grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
+                 unsigned* __restrict__ flags, int* __restrict__ status, int npad) {
+    extern __shared__ double smem[];
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, C = gridDim.x;
+    const int n = descs[0].n;
+    const int body0 = c * GB + 2 * warp;        // the warp's two bodies: body0, body0 + 1
+    const int my_body = body0 + lane / 3;       // integrator lanes 0..5
+    const int my_comp = lane % 3;
+    const bool integ = lane < 6 && my_body < n;
+
+    // per trajectory: pos[2][3*npad] (body-major x,y,z) then gm[npad]
+    auto s_pos = [&](int t, int buf) { return smem + (size_t)t * 7 * npad + (size_t)buf * 3 * npad; };
+    auto s_gm = [&](int t) { return smem + (size_t)t * 7 * npad + 6 * npad; };
+
+    TState ts[T];
+    if (tid == 0) s_abort = 0;
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        const TrajDesc& d = descs[t];
+        TState& s = ts[t];
+        s.n_dev = d.n_dev, s.kind = d.kind, s.P = d.planet, s.A = d.asteroid, s.DD = d.destroy_device;
+        s.step = d.step_begin, s.step_end = d.step_end;
+        s.min_d2 = d.ev->min_d2, s.argmin_step = d.ev->argmin_step, s.hit_step = d.ev->hit_step;
+        s.destroyed_step = d.ev->destroyed_step, s.cost = d.ev->cost;
+        s.q3_armed = (s.kind == NB_KIND_Q3) && s.DD >= 0 && s.DD < n && d.m[s.DD] != 0.0;
+        s.active = !((s.kind >= NB_KIND_Q2) && s.hit_step != -2);
+        s.cur = 0;
+        s.my_dev = -1, s.my_reach = -2, s.my_m0 = 0.0;
+        if (tid < s.n_dev) {
+            s.my_dev = d.dev_index[tid];
+            s.my_m0 = d.m[s.my_dev];
+            s.my_reach = d.ev->reach_step[tid];
+        }
+        s.fst_next = fst[s.step + 1];
+        s.v = s.q = 0.0;
+        if (integ) {
+            s.v = d.v[my_comp * n + my_body];
+            s.q = d.q[my_comp * n + my_body];
+        }
+        for (int i = tid; i < npad; i += GT) {
+            double x = 0, y = 0, z = 0, g = 0;
+            if (i < n) {
+                x = d.q[i], y = d.q[i + n], z = d.q[i + 2 * n];
+                g = d.is_device[i] ? 0.0 : gm_eff(d.m[i], false, 0.0);
+            }
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                double* p = s_pos(t, b) + 3 * i;
+                p[0] = x, p[1] = y, p[2] = z;
+            }
+            s_gm(t)[i] = g;
+        }
+    }
+    __syncthreads();
+
+    auto observe = [&](TState& s, int t) {
+        const double* pos = s_pos(t, s.cur);
+        const double* p = pos + 3 * s.P;
+        const double* a = pos + 3 * s.A;
+        const double px = p[0], py = p[1], pz = p[2];
+        const double d2 = dist2_rn(px, py, pz, a[0], a[1], a[2]);
+        if (d2 < s.min_d2) {  // hw5.cu:245-247
+            s.min_d2 = d2;
+            s.argmin_step = s.step;
+        }
+        if (s.kind == NB_KIND_Q2 && s.my_dev >= 0 && s.my_reach == -2) {  // hw5.cu:265-287
+            const double* dv = pos + 3 * s.my_dev;
+            const double md = __dmul_rn(MISSILE_STEP, (double)s.step);
+            if (dist2_rn(px, py, pz, dv[0], dv[1], dv[2]) < __dmul_rn(md, md)) s.my_reach = s.step;
+        }
+        if (s.kind >= NB_KIND_Q2) {
+            if (d2 < PLANET_RADIUS2) {  // nbody.cc:134, hw5.cu:295-298
+                s.hit_step = s.step;
+                s.active = false;
+            } else if (s.q3_armed && s.destroyed_step == -2) {  // hw5.cu:299-307
+                const double* dv = pos + 3 * s.DD;
+                const double md = __dmul_rn(MISSILE_STEP, (double)s.step);
+                if (dist2_rn(px, py, pz, dv[0], dv[1], dv[2]) < __dmul_rn(md, md)) {
+                    s.destroyed_step = s.step;
+                    s.cost = __dadd_rn(1e5, __dmul_rn(1e3, __dmul_rn((double)(s.step + 1), DT)));
+                }
+            }
+        }
+        if (s.step >= s.step_end) s.active = false;
+    };
+
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        if (descs[t].ev->steps_done < ts[t].step && ts[t].active) observe(ts[t], t);
+        if (ts[t].step >= ts[t].step_end) ts[t].active = false;
+    }
+
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < T; t++) any |= ts[t].active;
+
+    while (any) {
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            TState& s = ts[t];
+            if (!s.active) continue;  // uniform across the grid
+            const int st = ++s.step;
+            // (1) G*m_eff of the devices for this step (nbody.cc:61-64); a destroyed device has mass 0
+            if (s.my_dev >= 0) {
+                const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev == s.DD && s.destroyed_step != -2;
+                s_gm(t)[s.my_dev] = gm_eff(gone ? 0.0 : s.my_m0, true, s.fst_next);
+            }
+            __syncthreads();
+            s.fst_next = fst[st + 1];
+            // (2) forces on the warp's two bodies, j split over the lanes (nbody.cc:56-74)
+            const double* cpos = s_pos(t, s.cur);
+            const double* cg = s_gm(t);
+            const double* pa = cpos + 3 * min(body0, npad - 1);
+            const double* pb = cpos + 3 * min(body0 + 1, npad - 1);
+            const double xa = pa[0], ya = pa[1], za = pa[2], xb = pb[0], yb = pb[1], zb = pb[2];
+            double ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
+#pragma unroll 4
+            for (int j = lane; j < npad; j += 32) {
+                const double jx = cpos[3 * j], jy = cpos[3 * j + 1], jz = cpos[3 * j + 2], jg = cg[j];
+                pair<MATH>(xa, ya, za, jx, jy, jz, jg, ax0, ay0, az0);
+                pair<MATH>(xb, yb, zb, jx, jy, jz, jg, ax1, ay1, az1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ax0 += __shfl_xor_sync(0xffffffffu, ax0, o);
+                ay0 += __shfl_xor_sync(0xffffffffu, ay0, o);
+                az0 += __shfl_xor_sync(0xffffffffu, az0, o);
+                ax1 += __shfl_xor_sync(0xffffffffu, ax1, o);
+                ay1 += __shfl_xor_sync(0xffffffffu, ay1, o);
+                az1 += __shfl_xor_sync(0xffffffffu, az1, o);
+            }
+            // (3) v += a*dt; q += v*dt (nbody.cc:77-88): lane l < 6 owns (body0 + l/3, component l%3)
+            double* rec = gbuf + ((size_t)(st & 1) * T + t) * C * REC + (size_t)c * REC;
+            if (lane < 6) {
+                const double a = lane == 0 ? ax0 : lane == 1 ? ay0 : lane == 2 ? az0 : lane == 3 ? ax1 : lane == 4 ? ay1 : az1;
+                if (integ) kick_drift(a, s.v, s.q);
+                st_strong_d(rec + warp * 6 + lane, s.q);
+            }
+            __syncwarp();
+            if (lane == 0) st_release_u32(flags + ((size_t)t * C + c) * 4 + warp, (unsigned)st);
+            // (4) gather: warp w acquires producer blocks 32w..32w+31 (one flag word group per lane),
+            //     then copies their records coalesced into the other shared buffer
+            const int nxt = s.cur ^ 1;
+            {
+                const int pblk = 32 * warp + lane;
+                if (pblk < C) {
+                    const uint4* f = reinterpret_cast<const uint4*>(flags) + (size_t)t * C + pblk;
+                    const unsigned want = (unsigned)st;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        const uint4 fv = ld_acquire_u4(f);
+                        if (fv.x >= want && fv.y >= want && fv.z >= want && fv.w >= want) break;
+                        if (clock64() - t0 > SPIN_LIMIT) {
+                            s_abort = 1;
+                            atomicExch(status, 1);
+                            break;
+                        }
+                    }
+                }
+                __syncwarp();
+                const int first = 32 * warp * REC;                 // first double of this warp's producers
+                const int limit = C * REC;                         // doubles in the whole record array
+                const double* src = gbuf + ((size_t)(st & 1) * T + t) * C * REC;
+                double* dst = s_pos(t, nxt);
+                double2 r[REC / 2];
+#pragma unroll
+                for (int k = 0; k < REC / 2; k++) {
+                    const int o = first + 2 * (lane + 32 * k);
+                    if (o < limit) r[k] = ld_strong_d2(src + o);
+                }
+#pragma unroll
+                for (int k = 0; k < REC / 2; k++) {
+                    const int o = first + 2 * (lane + 32 * k);
+                    if (o < limit) *reinterpret_cast<double2*>(dst + o) = r[k];
+                }
+            }
+            __syncthreads();
+            if (s_abort) return;
+            s.cur = nxt;
+            // (5) observers of this step (hw5.cu:241-309), evaluated redundantly by every thread
+            observe(s, t);
+        }
+        any = false;
+#pragma unroll
+        for (int t = 0; t < T; t++) any |= ts[t].active;
+    }
+
+    // write back
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        const TrajDesc& d = descs[t];
+        TState& s = ts[t];
+        if (integ) {
+            d.q[my_comp * n + my_body] = s.q;
+            d.v[my_comp * n + my_body] = s.v;
+        }
+        if (c == 0) {
+            if (tid < s.n_dev) d.ev->reach_step[tid] = s.my_reach;
+            if (tid == 0) {
+                d.ev->min_d2 = s.min_d2;
+                d.ev->argmin_step = s.argmin_step;
+                d.ev->hit_step = s.hit_step;
+                d.ev->destroyed_step = s.destroyed_step;
+                d.ev->cost = s.cost;
+                d.ev->steps_done = s.step;
+                d.ev->n_reach = s.n_dev;
+                if (s.kind == NB_KIND_Q3 && s.destroyed_step != -2) d.m[s.DD] = 0.0;  // hw5.cu:306
+            }
+        }
+    }
+}
+
+int blocks_for(int n) { return (n + GB - 1) / GB; }
+int npad_for(int n) { return ((blocks_for(n) * GB + 31) / 32) * 32; }
+size_t smem_for(int n, int T) { return (size_t)T * 7 * npad_for(n) * sizeof(double); }
+
+struct WsLayout {
+    size_t gbuf_bytes, flags_bytes, total;
+};
+WsLayout ws_layout(int n, int T) {
+    WsLayout w;
+    const size_t C = blocks_for(n);
+    w.gbuf_bytes = 2 * (size_t)T * C * REC * sizeof(double);
+    w.flags_bytes = (size_t)T * C * 4 * sizeof(unsigned);
+    w.total = w.gbuf_bytes + w.flags_bytes + 256;
+    return w;
+}
+
+template <int MATH, int T>
+int launch_t(int n, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
+    const int C = blocks_for(n), npad = npad_for(n);
+    const size_t smem = smem_for(n, T);
+    const WsLayout w = ws_layout(n, T);
+    double* gbuf = (double*)ws;
+    unsigned* flags = (unsigned*)((char*)ws + w.gbuf_bytes);
+    int* status = (int*)((char*)ws + w.gbuf_bytes + w.flags_bytes);
+    auto kern = grid_traj_kernel<MATH, T>;
+    NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NB_CUDA(cudaMemsetAsync(flags, 0, w.flags_bytes + 256, stream));
+    int npad_arg = npad;
+    void* args[] = {(void*)&descs, (void*)&fst, (void*)&gbuf, (void*)&flags, (void*)&status, (void*)&npad_arg};
+    NB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(C), dim3(GT), args, smem, stream));
+    count_launch();
+    int h_status = 0;
+    NB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    NB_CUDA(cudaStreamSynchronize(stream));
+    if (h_status != 0) {
+        set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
+        return NB_ERR_CUDA;
+    }
+    return NB_OK;
+}
+
+template <int MATH>
+int launch_m(int T, int n, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
+    switch (T) {
+        case 1: return launch_t<MATH, 1>(n, descs, fst, ws, stream);
+        case 2: return launch_t<MATH, 2>(n, descs, fst, ws, stream);
+        case 3: return launch_t<MATH, 3>(n, descs, fst, ws, stream);
+        default: return launch_t<MATH, 4>(n, descs, fst, ws, stream);
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// the largest group of trajectories one launch takes for this n (shared-memory bound)
+static int group_size(int n) {
+    int T = MAX_T;
+    while (T > 1 && smem_for(n, T) > 220 * 1024) T--;
+    return T;
+}
+
+bool grid_traj_supported(int gpu, int n, int n_traj) {
+    (void)n_traj;
+    static const int enabled = env_int("NB_GRID", 1);
+    static const int min_n = env_int("NB_GRID_MIN_N", 256);
+    if (!enabled || n < min_n || n > NB_MAX_SMALL_N) return false;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, gpu) != cudaSuccess) return false;
+    if (!p.cooperativeLaunch) return false;
+    if (blocks_for(n) > p.multiProcessorCount) return false;
+    if (smem_for(n, 1) > (size_t)p.sharedMemPerBlockOptin) return false;
+    return true;
+}
+
+size_t grid_traj_workspace_bytes(int n, int n_traj) {
+    (void)n_traj;
+    return ws_layout(n, MAX_T).total;
+}
+
+int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs, const double* fst, int gpu, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
+    (void)gpu;
+    if (ws_bytes < ws_layout(n, MAX_T).total) return NB_ERR_ARG;
+    const int G = group_size(n);
+    for (int t0 = 0; t0 < n_traj; t0 += G) {  // groups of up to G trajectories run in lock step
+        const int T = n_traj - t0 < G ? n_traj - t0 : G;
+        // STRICT never comes here: its ascending-j sum is the single-block kernel's (nb_host.cu)
+        if (math != NB_MATH_FAST) return NB_ERR_UNSUPPORTED;
+        int rc = launch_m<MATH_FAST>(T, n, descs + t0, fst, ws, stream);
+        if (rc) return rc;
+    }
+    return NB_OK;
+}
+
 }  // namespace nb

@@ -190,7 +190,7 @@ struct DeviceBatch {
         NB_CUDA(cudaSetDevice(gpu));
         NB_CUDA(cudaMemcpyAsync(descs, h_descs.data(), S * sizeof(TrajDesc), cudaMemcpyHostToDevice, stream));
         NB_CUDA(cudaEventRecord(e0, stream));
-        if (allow_grid && grid_traj_supported(gpu, n, S)) {
+        if (allow_grid && math == NB_MATH_FAST && grid_traj_supported(gpu, n, S)) {
             size_t need = grid_traj_workspace_bytes(n, S);
             if (need > grid_ws_bytes) {
                 if (grid_ws) NB_CUDA(cudaFree(grid_ws));
@@ -390,69 +390,67 @@ int nb_run_steps(int gpu, int math, int n, double* q, double* v, const double* m
 // ---- the three queries -------------------------------------------------------------------------------
 // Ensemble scheduler: Q1, Q2 and one Q3 trajectory per device are independent (each Q3 trajectory is
 // re-simulated from step 0 with identical arithmetic, so its prefix equals Q2's: no snapshot
-// transport, no dependency on Q2 — SURVEY §7.2).  Trajectory t goes to gpus[t % n_gpus]; each GPU
-// runs its share as ONE launch from its own host thread; no collective, only scalars come back.
-int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int math, nb_answer* ans) {
-    if (!sys || !ans || !sys->q || !sys->v || !sys->m || !sys->is_device || sys->n < 1 || n_gpus < 1 || n_steps < 0)
-        return NB_ERR_ARG;
+// transport, no dependency on Q2 — SURVEY §7.2).  Trajectory t goes to part t % n_parts; each part
+// runs its share as ONE launch on its GPU; no collective, only nb_events structs come back.
+//   trajectory 0 = Q1, 1 = Q2, 2+k = Q3 with device k destroyed.
+static int solve_jobs(const nb_system* sys, std::vector<int>& devs) {
+    if (!sys || !sys->q || !sys->v || !sys->m || !sys->is_device || sys->n < 1) return NB_ERR_ARG;
     if (sys->n > NB_MAX_SMALL_N) return NB_ERR_UNSUPPORTED;
     if (sys->planet < 0 || sys->planet >= sys->n || sys->asteroid < 0 || sys->asteroid >= sys->n) return NB_ERR_ARG;
-    auto t_begin = std::chrono::steady_clock::now();
-    const int n = sys->n;
-    std::vector<int> gl(n_gpus);
-    for (int g = 0; g < n_gpus; g++) {
-        gl[g] = gpus ? gpus[g] : g;
-        int rc = nb::check_gpu(gl[g]);
-        if (rc) return rc;
-    }
-    std::vector<int> devs;
-    for (int i = 0; i < n; i++)
+    devs.clear();
+    for (int i = 0; i < sys->n; i++)
         if (sys->is_device[i]) devs.push_back(i);
+    if ((int)devs.size() > NB_MAX_DEVICES) return NB_ERR_UNSUPPORTED;
+    return NB_OK;
+}
+
+int nb_solve_trajectory_count(const nb_system* sys, int* count) {
+    std::vector<int> devs;
+    int rc = solve_jobs(sys, devs);
+    if (rc) return rc;
+    if (!count) return NB_ERR_ARG;
+    *count = 2 + (int)devs.size();
+    return NB_OK;
+}
+
+int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n_steps, int math, nb_events* evs,
+                     double* gpu_seconds, long long* pair_interactions) {
+    std::vector<int> devs;
+    int rc = solve_jobs(sys, devs);
+    if (rc) return rc;
+    if (!evs || n_parts < 1 || part < 0 || part >= n_parts || n_steps < 0) return NB_ERR_ARG;
+    if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
+    rc = nb::check_gpu(gpu);
+    if (rc) return rc;
+    const int T = 2 + (int)devs.size();
+    std::vector<int> mine;
+    for (int t = part; t < T; t += n_parts) mine.push_back(t);
+    if (gpu_seconds) *gpu_seconds = 0;
+    if (pair_interactions) *pair_interactions = 0;
+    if (mine.empty()) return NB_OK;
+    DeviceBatch b;
+    rc = b.init(gpu, (int)mine.size(), sys->n, math);
+    for (size_t s = 0; s < mine.size() && !rc; s++) {
+        const int t = mine[s];
+        const int kind = t == 0 ? NB_KIND_Q1 : (t == 1 ? NB_KIND_Q2 : NB_KIND_Q3);
+        rc = b.set_system((int)s, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid, kind,
+                          t >= 2 ? devs[t - 2] : -1, 0);
+    }
+    if (!rc) rc = b.run(n_steps, true);
+    if (!rc)
+        for (size_t s = 0; s < mine.size(); s++) evs[mine[s]] = b.h_ev[s];
+    if (gpu_seconds) *gpu_seconds = b.gpu_seconds;
+    if (pair_interactions) *pair_interactions = b.pairs;
+    b.release();
+    return rc;
+}
+
+int nb_solve_combine(const nb_system* sys, const nb_events* evs, nb_answer* ans) {
+    std::vector<int> devs;
+    int rc = solve_jobs(sys, devs);
+    if (rc) return rc;
+    if (!evs || !ans) return NB_ERR_ARG;
     const int dc = (int)devs.size();
-    if (dc > NB_MAX_DEVICES) return NB_ERR_UNSUPPORTED;
-
-    struct Job {
-        int kind, destroy;
-    };
-    std::vector<Job> jobs;
-    jobs.push_back({NB_KIND_Q1, -1});
-    jobs.push_back({NB_KIND_Q2, -1});
-    for (int k = 0; k < dc; k++) jobs.push_back({NB_KIND_Q3, devs[k]});
-    const int T = (int)jobs.size();
-    const int G = n_gpus < T ? n_gpus : T;
-    std::vector<nb_events> evs(T);
-    std::vector<int> rcs(G, 0);
-    std::vector<std::string> details(G);
-    std::vector<double> secs(G, 0.0);
-    std::vector<long long> pairs(G, 0);
-
-    auto worker = [&](int g) {
-        std::vector<int> mine;
-        for (int t = g; t < T; t += G) mine.push_back(t);
-        DeviceBatch b;
-        int rc = b.init(gl[g], (int)mine.size(), n, math);
-        for (size_t s = 0; s < mine.size() && !rc; s++)
-            rc = b.set_system((int)s, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid,
-                              jobs[mine[s]].kind, jobs[mine[s]].destroy, 0);
-        if (!rc) rc = b.run(n_steps, true);
-        if (!rc)
-            for (size_t s = 0; s < mine.size(); s++) evs[mine[s]] = b.h_ev[s];
-        secs[g] = b.gpu_seconds;
-        pairs[g] = b.pairs;
-        b.release();
-        rcs[g] = rc;
-        if (rc) details[g] = nb::g_detail;
-    };
-    std::vector<std::thread> th;
-    for (int g = 1; g < G; g++) th.emplace_back(worker, g);
-    worker(0);
-    for (auto& t : th) t.join();
-    for (int g = 0; g < G; g++)
-        if (rcs[g]) {
-            nb::set_error_detail(details[g]);
-            return rcs[g];
-        }
-
     memset(ans, 0, sizeof *ans);
     ans->min_dist = sqrt(evs[0].min_d2);  // hw5.cu:407
     ans->argmin_step = evs[0].argmin_step;
@@ -480,11 +478,51 @@ int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int
             }
         }
     }
+    ans->n_trajectories = 2 + dc;
+    return NB_OK;
+}
+
+int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int math, nb_answer* ans) {
+    std::vector<int> devs;
+    int rc = solve_jobs(sys, devs);
+    if (rc) return rc;
+    if (!ans || n_gpus < 1 || n_steps < 0) return NB_ERR_ARG;
+    auto t_begin = std::chrono::steady_clock::now();
+    const int T = 2 + (int)devs.size();
+    const int G = n_gpus < T ? n_gpus : T;
+    std::vector<int> gl(G);
+    for (int g = 0; g < G; g++) {
+        gl[g] = gpus ? gpus[g] : g;
+        rc = nb::check_gpu(gl[g]);
+        if (rc) return rc;
+    }
+    std::vector<nb_events> evs(T);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> details(G);
+    std::vector<double> secs(G, 0.0);
+    std::vector<long long> pairs(G, 0);
+    std::vector<std::vector<nb_events>> part_evs(G, std::vector<nb_events>(T));
+    auto worker = [&](int g) {
+        rcs[g] = nb_solve_partial(sys, gl[g], g, G, n_steps, math, part_evs[g].data(), &secs[g], &pairs[g]);
+        if (rcs[g]) details[g] = nb::g_detail;
+    };
+    std::vector<std::thread> th;  // one host thread per GPU (hw5.cu:566-567, 587-588)
+    for (int g = 1; g < G; g++) th.emplace_back(worker, g);
+    worker(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++) {
+        if (rcs[g]) {
+            nb::set_error_detail(details[g]);
+            return rcs[g];
+        }
+        for (int t = g; t < T; t += G) evs[t] = part_evs[g][t];
+    }
+    rc = nb_solve_combine(sys, evs.data(), ans);
+    if (rc) return rc;
     for (int g = 0; g < G; g++) {
         if (secs[g] > ans->gpu_seconds) ans->gpu_seconds = secs[g];
         ans->pair_interactions += pairs[g];
     }
-    ans->n_trajectories = T;
     ans->n_gpus_used = G;
     ans->wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     return NB_OK;

@@ -170,13 +170,20 @@ __global__ void large_unpack_kernel(int n, const double4* __restrict__ pos4, dou
     q[i] = p.x, q[i + n] = p.y, q[i + 2 * n] = p.z;
 }
 
+// optional per-thread profiling of the acceleration kernel (nb_profile_enable / nb_profile_read)
+struct Prof {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+};
+thread_local Prof g_prof;
+
 int g_ipt = 0;     // 0 = not read yet
 int g_jsplit = -1;  // -1 = not read yet, 0 = heuristic
 void read_env() {
     if (g_ipt == 0) {
         const char* e = getenv("NB_LARGE_IPT");
-        int v = e ? atoi(e) : 2;
-        g_ipt = (v == 1 || v == 2 || v == 4) ? v : 2;
+        int v = e ? atoi(e) : 4;  // measured on B200 (profiles/r01_probe.md): IPT 4 >= 2 > 1
+        g_ipt = (v == 1 || v == 2 || v == 4) ? v : 4;
     }
     if (g_jsplit < 0) {
         const char* e = getenv("NB_LARGE_JSPLIT");
@@ -190,8 +197,9 @@ int pick_jsplit(int math, int n, int i_count, int ipt) {
     if (g_jsplit > 0) return g_jsplit;
     const int iblocks = (i_count + LT * ipt - 1) / (LT * ipt);
     int js = 1;
-    // enough equal pieces for ~4 full waves of 148 SMs x 7 resident blocks, >= 2 tiles per piece
-    while (js < MAX_JSPLIT && iblocks * js < 4 * 148 * 7 && n / (js * 2) >= 2 * TJ) js *= 2;
+    // enough equal pieces (>= ~14 per SM) that the 148 SMs finish together, >= 2 tiles per piece;
+    // measured on B200: 65 536 bodies, IPT 4: 1 split 43.8 %, 8 splits 54.6 %, 16 splits 54.9 % of peak
+    while (js < MAX_JSPLIT && iblocks * js < 14 * 148 && n / (js * 2) >= 2 * TJ) js *= 2;
     return js;
 }
 
@@ -255,12 +263,22 @@ int nb_large_step(int math, int step, int n, int i_begin, int i_count, const dou
     const int nsplit = (n + jps - 1) / jps;
     dim3 grid((i_count + LT * ipt - 1) / (LT * ipt), nsplit);
     cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (g_prof.on) {
+        NB_CUDA(cudaEventCreate(&pe0));
+        NB_CUDA(cudaEventCreate(&pe1));
+        NB_CUDA(cudaEventRecord(pe0, st));
+    }
     int rc = math == NB_MATH_STRICT
                  ? launch_accel<MATH_STRICT>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
                                              (double*)scratch_dev)
                  : launch_accel<MATH_FAST>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
                                            (double*)scratch_dev);
     if (rc) return rc;
+    if (g_prof.on) {
+        NB_CUDA(cudaEventRecord(pe1, st));
+        g_prof.evs.emplace_back(pe0, pe1);
+    }
     const double fst_next = fst_table_host(step + 2)[step + 1];
     large_integrate_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, (double4*)pos4_out_dev,
                                                                   vel_dev, m0_dev, is_device_dev,
@@ -268,6 +286,26 @@ int nb_large_step(int math, int step, int n, int i_begin, int i_count, const dou
                                                                   fst_next, math == NB_MATH_STRICT);
     count_launch();
     NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+int nb_profile_enable(int on) {
+    for (auto& p : g_prof.evs) cudaEventDestroy(p.first), cudaEventDestroy(p.second);
+    g_prof.evs.clear();
+    g_prof.on = on != 0;
+    return NB_OK;
+}
+
+int nb_profile_read(double* accel_ms, long long* accel_launches) {
+    double total = 0;
+    for (auto& p : g_prof.evs) {
+        NB_CUDA(cudaEventSynchronize(p.second));
+        float ms = 0;
+        NB_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        total += ms;
+    }
+    if (accel_ms) *accel_ms = total;
+    if (accel_launches) *accel_launches = (long long)g_prof.evs.size();
     return NB_OK;
 }
 

@@ -148,6 +148,41 @@ class ShardedSystem:
                 dist.all_gather_into_tensor(dst.view(-1), shard, group=self.group)
             self.cur ^= 1
 
+    def step_host(self, q_host, v_host):
+        """The run_step operator with HOST buffers (nbody.cc:51-54 signature, sharded): q_host is a
+        pinned planar [3n] tensor holding ALL positions (in: state before the step, out: after),
+        v_host a pinned planar [3, i_count] tensor with this rank's velocities (in/out).  Every call
+        copies host->device, packs, steps, all-gathers, unpacks and copies device->host."""
+        import ctypes as C
+
+        torch = self.torch
+        from . import _check, lib
+
+        L = lib()
+        if not hasattr(self, "_qd"):
+            self._qd = torch.empty(3 * self.n, dtype=torch.float64, device=self.device)
+        st = torch.cuda.current_stream().cuda_stream
+        self._qd.copy_(q_host, non_blocking=True)
+        self.vel.copy_(v_host, non_blocking=True)
+        self.step += 1
+        src, dst = self.pos4[self.cur], self.pos4[self.cur ^ 1]
+        _check(L.nb_large_pack(self.math, self.n, C.c_void_p(self._qd.data_ptr()), C.c_void_p(self.m0.data_ptr()),
+                               C.c_void_p(self.isdev.data_ptr()), self.step, C.c_void_p(src.data_ptr()), C.c_void_p(st)))
+        self.local_step(self.step, self.n, self.i_begin, self.i_count, src, dst, self.vel, self.m0, self.isdev,
+                        self.scratch)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            shard = dst[self.i_begin:self.i_begin + self.i_count].view(-1)
+            dist.all_gather_into_tensor(dst.view(-1), shard, group=self.group)
+        self.cur ^= 1
+        _check(L.nb_large_unpack(self.n, C.c_void_p(dst.data_ptr()), C.c_void_p(self._qd.data_ptr()), C.c_void_p(st)))
+        q_host.copy_(self._qd, non_blocking=True)
+        v_host.copy_(self.vel, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h2d = q_host.numel() * 8 + v_host.numel() * 8
+        return h2d, h2d  # bytes host->device, device->host
+
     def positions(self):
         """Planar q[3n] of all bodies (host numpy)."""
         p = self.pos4[self.cur].detach().to("cpu").numpy()

@@ -197,6 +197,38 @@ def test_error_codes_on_gpu(nb):
     assert e.value.code == nb.NB_ERR_ARG
 
 
+def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
+    """The whole-GPU cooperative kernel is normally used from n = 256 up; force it on b100 / b200
+    (13 / 25 blocks, ragged last block) in a subprocess and compare with the goldens and the KATs."""
+    import sys
+    code = (
+        "import importlib, json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "nb = importlib.import_module('nthu_ipc_nbody-simulation_b200')\n"
+        "out = {}\n"
+        "for case in ('b100', 'b200', 'b90'):\n"
+        "    s = nb.read_input(%r + '/' + case + '.in')\n"
+        "    a = nb.solve(s, gpus=[0])\n"
+        "    out[case] = dict(text=nb.format_output(a.min_dist, a.hit_time_step, a.gravity_device_id, a.missile_cost),\n"
+        "                     argmin=a.argmin_step, reach=list(a.reach_step[:a.n_devices]), q3=list(a.q3_hit_step[:a.n_devices]))\n"
+        "print(json.dumps(out))\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                        os.path.join(GOLDEN, "testcases"))
+    env = dict(os.environ, NB_GRID_MIN_N="16")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    out = json.loads(r.stdout.decode().strip().split("\n")[-1])
+    kats = json.load(open(os.path.join(GOLDEN, "oracle_kats.json")))
+    for case, o in out.items():
+        g = golden_lines(case)
+        a, b, c = o["text"].split("\n")[:3]
+        assert b == str(g["hit_time_step"]) and c == g["text"].split("\n")[2]
+        assert abs(float(a) - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+        k = kats[case]
+        assert o["argmin"] == k["argmin_step"]
+        assert o["reach"] == [d["reach_step"] for d in k["devices"]]
+        assert o["q3"] == [d["q3_hit_step"] for d in k["devices"]]
+
+
 # ---- ensembles ---------------------------------------------------------------------------------------
 def test_ensemble_members_match_individual_runs(nb, oracle):
     """SURVEY §8d config C4 in miniature: member k = the golden system with velocities scaled by (1 + 1e-9 k)."""

@@ -15,6 +15,11 @@ def peak():
     print("fp64 peak TF/s:", nb.fp64_peak(0), flush=True)
 
 
+def peakv():
+    for v in (0, 1, 2):
+        print("fp64 peak variant %d (0: reg*UR+reg.reuse, 1: 3 distinct regs, 2: shared multiplicand): %.2f TF/s" % (v, nb.fp64_peak(0, v)), flush=True)
+
+
 def traj(case="b1024", steps=2000):
     s = nb.read_input(os.path.join(G, case + ".in"))
     steps = int(steps)

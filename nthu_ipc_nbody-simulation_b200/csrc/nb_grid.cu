@@ -11,17 +11,24 @@
 // shared-memory traffic stays at half the FP64 issue rate.  A 5-round xor butterfly combines the
 // lanes; lanes 0-5 each integrate one (body, component) and publish the new coordinate.
 //
-// Exchange (the step's only grid-wide dependency): every block publishes its 8 new positions
-// (192 B, body-major x,y,z) into a double-buffered global record array (L2 resident) and each warp
-// releases a step-counter flag; in every block warp w acquires the flags of producer blocks
-// 32w..32w+31 (one per lane) and then copies their records, coalesced 16 B per lane, into the
-// block's shared memory (raw records, double-buffered by step parity; lanes at consecutive j read
-// them at a 24 B stride, which is bank-conflict free for 8 B accesses).  One __syncthreads later
-// every block holds all positions of the new step.  No grid-wide barrier object, no atomics: 2 block barriers
-// and one release/acquire hop per step.  Spins are bounded (clock64) and raise `status`.
+// Exchange (the step's only grid-wide dependency), measured design (tools/microbench/exchange_bench.cu,
+// profiles/r01_exchange_microbench.md): on B200 a release/acquire hop costs ~0.4-0.5 us per fence
+// (MEMBAR.ALL.GPU) and an atomic-counter grid barrier ~1.5 us, while an un-fenced store -> poll hop is
+// ~0.37 us.  So there are no fences, no atomics and no barrier object: every body is published as one
+// naturally aligned 32-byte sector {x, y, z, step tag} with a single 256-bit store, into a global
+// record array double-buffered by step parity (L2 resident).  A sector is the unit the L2 reads and
+// writes, so a reader sees it entirely old or entirely new and the tag validates the data it travels
+// with; no ordering between different sectors is assumed anywhere.  Thread p of every block polls the
+// tag of producer p's last sector (the block's 8 sectors leave in one store instruction), then the
+// block fetches all sectors coalesced with 256-bit loads, re-reading any sector whose tag is still
+// old, and scatters x,y,z into shared memory (24 B stride: bank-conflict free for 8 B accesses).
+// Reuse of a parity buffer is safe without fences: a block overwrites step s-2's sectors only after
+// it has consumed every block's step s-1 sectors, which each block publishes only after its own reads
+// of step s-2 have completed (data dependence).  Spins are bounded (clock64) and raise `status`.
 //
 // Co-residency of all blocks is guaranteed by the cooperative launch (grid <= SM count, 1 block/SM).
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "nb_internal.h"
@@ -36,21 +43,18 @@ constexpr int REC = GB * 3;   // doubles per block record
 constexpr int MAX_T = 4;      // trajectories per launch (shared memory: 56 B x npad each)
 constexpr long long SPIN_LIMIT = 4000000000LL;  // ~2 s of SM clocks
 
-__device__ __forceinline__ uint4 ld_acquire_u4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+__device__ __forceinline__ double ld_strong_d(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// one naturally aligned 32-byte sector per access (SASS LDG/STG.E.ENL2.256): the unit the L2 reads and
+// writes, so a sector is observed either entirely old or entirely new
+__device__ __forceinline__ void ld_sector(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
-__device__ __forceinline__ double2 ld_strong_d2(const double* p) {
-    double2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_strong_d(double* p, double v) {
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+__device__ __forceinline__ void st_sector(double* p, double a, double b, double c, double d) {
+    asm volatile("st.relaxed.gpu.global.v4.f64 [%4], {%0,%1,%2,%3};" ::"d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
 struct TState {  // per trajectory, per thread (registers after unrolling)
@@ -68,12 +72,14 @@ struct TState {  // per trajectory, per thread (registers after unrolling)
     int cur;
 };
 
-template <int MATH, int T>
+// PROFILE: block 0 thread 0 accumulates clock64 per phase into prof[0..7] (NB_GRID_PROFILE=1, T == 1 only)
+template <int MATH, int T, bool PROFILE>
 __global__ void __launch_bounds__(GT, 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 unsigned* __restrict__ flags, int* __restrict__ status, int npad) {
+                 long long* __restrict__ prof, int* __restrict__ status, int npad) {
     extern __shared__ double smem[];
     __shared__ int s_abort;
+    __shared__ double s_stage[REC];  // the block's 8 new positions, staged for the one-instruction publish
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, C = gridDim.x;
     const int n = descs[0].n;
@@ -87,6 +93,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     auto s_gm = [&](int t) { return smem + (size_t)t * 7 * npad + 6 * npad; };
 
     TState ts[T];
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+    auto tick = [&](int phase) {
+        if (PROFILE) {
+            const long long now = clock64();
+            pacc[phase] += now - pt;
+            pt = now;
+        }
+    };
     if (tid == 0) s_abort = 0;
 #pragma unroll
     for (int t = 0; t < T; t++) {
@@ -167,6 +181,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     bool any = false;
 #pragma unroll
     for (int t = 0; t < T; t++) any |= ts[t].active;
+    long long g0 = 0, c0 = 0;
+    if (PROFILE) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        c0 = clock64();
+    }
 
     while (any) {
 #pragma unroll
@@ -174,12 +193,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             TState& s = ts[t];
             if (!s.active) continue;  // uniform across the grid
             const int st = ++s.step;
+            if (PROFILE) pt = clock64();
             // (1) G*m_eff of the devices for this step (nbody.cc:61-64); a destroyed device has mass 0
             if (s.my_dev >= 0) {
                 const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev == s.DD && s.destroyed_step != -2;
                 s_gm(t)[s.my_dev] = gm_eff(gone ? 0.0 : s.my_m0, true, s.fst_next);
             }
             __syncthreads();
+            tick(0);
             s.fst_next = fst[st + 1];
             // (2) forces on the warp's two bodies, j split over the lanes (nbody.cc:56-74)
             const double* cpos = s_pos(t, s.cur);
@@ -194,6 +215,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 pair<MATH>(xa, ya, za, jx, jy, jz, jg, ax0, ay0, az0);
                 pair<MATH>(xb, yb, zb, jx, jy, jz, jg, ax1, ay1, az1);
             }
+            tick(1);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 ax0 += __shfl_xor_sync(0xffffffffu, ax0, o);
@@ -204,61 +226,87 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 az1 += __shfl_xor_sync(0xffffffffu, az1, o);
             }
             // (3) v += a*dt; q += v*dt (nbody.cc:77-88): lane l < 6 owns (body0 + l/3, component l%3)
-            double* rec = gbuf + ((size_t)(st & 1) * T + t) * C * REC + (size_t)c * REC;
             if (lane < 6) {
                 const double a = lane == 0 ? ax0 : lane == 1 ? ay0 : lane == 2 ? az0 : lane == 3 ? ax1 : lane == 4 ? ay1 : az1;
                 if (integ) kick_drift(a, s.v, s.q);
-                st_strong_d(rec + warp * 6 + lane, s.q);
+                s_stage[warp * 6 + lane] = s.q;
             }
-            __syncwarp();
-            if (lane == 0) st_release_u32(flags + ((size_t)t * C + c) * 4 + warp, (unsigned)st);
-            // (4) gather: warp w acquires producer blocks 32w..32w+31 (one flag word group per lane),
-            //     then copies their records coalesced into the other shared buffer
+            __syncthreads();
+            // publish: lanes 0..7 of warp 0 write the block's 8 tagged sectors {x, y, z, step} in ONE
+            // store instruction; no fence: every sector validates itself (see the header comment)
+            double* sec = gbuf + ((size_t)(st & 1) * T + t) * C * GB * 4;
+            const long long tag = (long long)st;
+            if (tid < GB)
+                st_sector(sec + (size_t)(c * GB + tid) * 4, s_stage[3 * tid], s_stage[3 * tid + 1], s_stage[3 * tid + 2],
+                          __longlong_as_double(tag));
+            tick(2);
+            // (4a) wait until every producer's LAST sector carries this step's tag (one 8-byte poll per producer)
             const int nxt = s.cur ^ 1;
+            if (tid < C) {
+                const double* sentinel = sec + ((size_t)tid * GB + GB - 1) * 4 + 3;
+                const long long t0 = clock64();
+                while (__double_as_longlong(ld_strong_d(sentinel)) != tag) {
+                    if (clock64() - t0 > SPIN_LIMIT) {
+                        s_abort = 1;
+                        atomicExch(status, 1);
+                        break;
+                    }
+                }
+            }
+            tick(3);
+            __syncthreads();
+            if (s_abort) return;
+            tick(4);
+            // (4b) fetch all sectors, coalesced (consecutive lanes, consecutive sectors); a sector whose tag is
+            //      not this step's yet (its store was overtaken by the sentinel's) is simply read again
             {
-                const int pblk = 32 * warp + lane;
-                if (pblk < C) {
-                    const uint4* f = reinterpret_cast<const uint4*>(flags) + (size_t)t * C + pblk;
-                    const unsigned want = (unsigned)st;
-                    const long long t0 = clock64();
-                    for (;;) {
-                        const uint4 fv = ld_acquire_u4(f);
-                        if (fv.x >= want && fv.y >= want && fv.z >= want && fv.w >= want) break;
-                        if (clock64() - t0 > SPIN_LIMIT) {
-                            s_abort = 1;
-                            atomicExch(status, 1);
-                            break;
+                double* dst = s_pos(t, nxt);
+                const int nsec = C * GB;
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0 += 4) {
+                    double x[4], y[4], z[4], g[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int b = tid + GT * (k0 + k);
+                        if (b < nsec) ld_sector(sec + (size_t)b * 4, x[k], y[k], z[k], g[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int b = tid + GT * (k0 + k);
+                        if (b < nsec) {
+                            const long long t0 = clock64();
+                            while (__double_as_longlong(g[k]) != tag) {
+                                ld_sector(sec + (size_t)b * 4, x[k], y[k], z[k], g[k]);
+                                if (clock64() - t0 > SPIN_LIMIT) {
+                                    s_abort = 1;
+                                    atomicExch(status, 1);
+                                    break;
+                                }
+                            }
+                            dst[3 * b] = x[k], dst[3 * b + 1] = y[k], dst[3 * b + 2] = z[k];
                         }
                     }
                 }
-                __syncwarp();
-                const int first = 32 * warp * REC;                 // first double of this warp's producers
-                const int limit = C * REC;                         // doubles in the whole record array
-                const double* src = gbuf + ((size_t)(st & 1) * T + t) * C * REC;
-                double* dst = s_pos(t, nxt);
-                double2 r[REC / 2];
-#pragma unroll
-                for (int k = 0; k < REC / 2; k++) {
-                    const int o = first + 2 * (lane + 32 * k);
-                    if (o < limit) r[k] = ld_strong_d2(src + o);
-                }
-#pragma unroll
-                for (int k = 0; k < REC / 2; k++) {
-                    const int o = first + 2 * (lane + 32 * k);
-                    if (o < limit) *reinterpret_cast<double2*>(dst + o) = r[k];
-                }
             }
+            tick(5);
             __syncthreads();
             if (s_abort) return;
             s.cur = nxt;
             // (5) observers of this step (hw5.cu:241-309), evaluated redundantly by every thread
             observe(s, t);
+            tick(6);
         }
         any = false;
 #pragma unroll
         for (int t = 0; t < T; t++) any |= ts[t].active;
     }
 
+    if (PROFILE && tid == 0 && c == 0) {
+        long long g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        for (int k = 0; k < 7; k++) prof[k] = pacc[k];
+        prof[7] = (clock64() - c0) * 1000 / (g1 - g0 > 0 ? g1 - g0 : 1);  // SM MHz over the step loop
+    }
     // write back
 #pragma unroll
     for (int t = 0; t < T; t++) {
@@ -284,6 +332,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     }
 }
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int blocks_for(int n) { return (n + GB - 1) / GB; }
 int npad_for(int n) { return ((blocks_for(n) * GB + 31) / 32) * 32; }
 size_t smem_for(int n, int T) { return (size_t)T * 7 * npad_for(n) * sizeof(double); }
@@ -294,8 +347,8 @@ struct WsLayout {
 WsLayout ws_layout(int n, int T) {
     WsLayout w;
     const size_t C = blocks_for(n);
-    w.gbuf_bytes = 2 * (size_t)T * C * REC * sizeof(double);
-    w.flags_bytes = (size_t)T * C * 4 * sizeof(unsigned);
+    w.gbuf_bytes = 2 * (size_t)T * C * GB * 4 * sizeof(double);  // [parity][T][C*8] sectors {x, y, z, step tag}
+    w.flags_bytes = 0;
     w.total = w.gbuf_bytes + w.flags_bytes + 256;
     return w;
 }
@@ -306,18 +359,26 @@ int launch_t(int n, const TrajDesc* descs, const double* fst, void* ws, cudaStre
     const size_t smem = smem_for(n, T);
     const WsLayout w = ws_layout(n, T);
     double* gbuf = (double*)ws;
-    unsigned* flags = (unsigned*)((char*)ws + w.gbuf_bytes);
-    int* status = (int*)((char*)ws + w.gbuf_bytes + w.flags_bytes);
-    auto kern = grid_traj_kernel<MATH, T>;
+    int* status = (int*)((char*)ws + w.gbuf_bytes);
+    long long* prof = (long long*)((char*)ws + w.gbuf_bytes + 64);
+    static const bool profile = env_int("NB_GRID_PROFILE", 0) != 0;
+    auto kern = (T == 1 && profile) ? grid_traj_kernel<MATH, T, (T == 1)> : grid_traj_kernel<MATH, T, false>;
     NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NB_CUDA(cudaMemsetAsync(flags, 0, w.flags_bytes + 256, stream));
+    NB_CUDA(cudaMemsetAsync(ws, 0, w.total, stream));  // tag 0 = no step; also clears status
     int npad_arg = npad;
-    void* args[] = {(void*)&descs, (void*)&fst, (void*)&gbuf, (void*)&flags, (void*)&status, (void*)&npad_arg};
+    void* args[] = {(void*)&descs, (void*)&fst, (void*)&gbuf, (void*)&prof, (void*)&status, (void*)&npad_arg};
     NB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(C), dim3(GT), args, smem, stream));
     count_launch();
     int h_status = 0;
     NB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, stream));
     NB_CUDA(cudaStreamSynchronize(stream));
+    if (T == 1 && profile) {
+        long long h[8];
+        NB_CUDA(cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "grid profile (clk, block 0 thread 0): gm+sync %lld | pairs %lld | reduce+integrate+publish %lld | "
+                        "sentinel wait %lld | sync %lld | fetch %lld | sync+observe %lld | SM clock %lld MHz\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
     if (h_status != 0) {
         set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
         return NB_ERR_CUDA;
@@ -333,11 +394,6 @@ int launch_m(int T, int n, const TrajDesc* descs, const double* fst, void* ws, c
         case 3: return launch_t<MATH, 3>(n, descs, fst, ws, stream);
         default: return launch_t<MATH, 4>(n, descs, fst, ws, stream);
     }
-}
-
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
 }
 
 }  // namespace

@@ -190,7 +190,10 @@ struct DeviceBatch {
         NB_CUDA(cudaSetDevice(gpu));
         NB_CUDA(cudaMemcpyAsync(descs, h_descs.data(), S * sizeof(TrajDesc), cudaMemcpyHostToDevice, stream));
         NB_CUDA(cudaEventRecord(e0, stream));
-        if (allow_grid && math == NB_MATH_FAST && grid_traj_supported(gpu, n, S)) {
+        int max_dev = 0;
+        for (int s = 0; s < S; s++) max_dev = h_descs[s].n_dev > max_dev ? h_descs[s].n_dev : max_dev;
+        // the grid kernel keeps one device per lane; STRICT needs the single block's ascending-j sum
+        if (allow_grid && math == NB_MATH_FAST && max_dev <= 32 && grid_traj_supported(gpu, n, S)) {
             size_t need = grid_traj_workspace_bytes(n, S);
             if (need > grid_ws_bytes) {
                 if (grid_ws) NB_CUDA(cudaFree(grid_ws));

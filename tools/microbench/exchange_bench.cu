@@ -72,6 +72,39 @@ __global__ void __launch_bounds__(GT, 1) bench(double* gbuf, unsigned* flags, in
             acc += dst[(tid * 7) % (C * REC)];
             continue;
         }
+        if (SCHEME == 11 || SCHEME == 14) {
+            // 11 = PULL: one shared record array of tagged sectors; lane p polls producer p's last sector, then loads its 8
+            // 14 = PUSH: every producer writes its 8 tagged sectors into EVERY consumer's private mailbox; consumers poll
+            //      only their own mailbox (each sector has one writer and one reader)
+            const long long tg = (long long)st;
+            if (SCHEME == 11) {
+                double* g = gbuf + (size_t)par * C * 32;
+                if (tid < 8) st256(g + (c * 8 + tid) * 4, acc, acc + 1, acc + 2, __longlong_as_double(tg));
+            } else {
+                // mailbox[consumer][parity][producer][8 sectors]; thread t writes consumer t, all 8 sectors of this block
+                for (int q = tid; q < C; q += GT) {
+                    double* g = gbuf + ((size_t)q * 2 + par) * C * 32 + (size_t)c * 32;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) st256(g + k * 4, acc, acc + 1, acc + 2, __longlong_as_double(tg));
+                }
+            }
+            if (tid < C) {
+                const double* g = SCHEME == 11 ? gbuf + (size_t)par * C * 32 + (size_t)tid * 32
+                                               : gbuf + ((size_t)c * 2 + par) * C * 32 + (size_t)tid * 32;
+                double x[8], y[8], z[8], tag[8];
+                do { asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(tag[7]) : "l"(g + 31) : "memory"); } while (__double_as_longlong(tag[7]) != tg);
+#pragma unroll
+                for (int k = 0; k < 8; k++) ld256(g + k * 4, x[k], y[k], z[k], tag[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    while (__double_as_longlong(tag[k]) != tg) ld256(g + k * 4, x[k], y[k], z[k], tag[k]);
+                    dst[3 * (k * C + tid)] = x[k], dst[3 * (k * C + tid) + 1] = y[k], dst[3 * (k * C + tid) + 2] = z[k];
+                }
+            }
+            __syncthreads();
+            acc += dst[(tid * 7) % (C * REC)];
+            continue;
+        }
         if (SCHEME == 8) {  // data load only, no synchronisation (lower bound of the 24 KB fetch)
             const double* src = gbuf + (size_t)par * C * REC;
             for (int o = 2 * tid; o < C * REC; o += 2 * GT) *reinterpret_cast<double2*>(dst + o) = ld_strong_d2(src + o);
@@ -225,7 +258,7 @@ void run(int C, int steps, int work, double* gbuf, unsigned* flags, double* sink
     size_t smem = 2 * (size_t)C * 32 * sizeof(double);
     cudaFuncSetAttribute(bench<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemset(flags, 0, 1 << 20);
-    cudaMemset(gbuf, 0, 1 << 22);
+    cudaMemset(gbuf, 0, 1 << 24);
     void* args[] = {&gbuf, &flags, &steps, &work, &sink, &cyc};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
@@ -247,9 +280,9 @@ int main(int argc, char** argv) {
     double *gbuf, *sink;
     unsigned* flags;
     long long* cyc;
-    cudaMalloc(&gbuf, 1 << 22), cudaMalloc(&sink, 8), cudaMalloc(&flags, 1 << 20), cudaMalloc(&cyc, 8);
+    cudaMalloc(&gbuf, 1 << 24), cudaMalloc(&sink, 8), cudaMalloc(&flags, 1 << 20), cudaMalloc(&cyc, 8);
     for (int work : {0}) {
-        for (int C : {2, 13, 32, 64, 128}) {
+        for (int C : {2, 32, 64, 128}) {
             run<0>(C, steps, work, gbuf, flags, sink, cyc);
             run<1>(C, steps, work, gbuf, flags, sink, cyc);
             run<6>(C, steps, work, gbuf, flags, sink, cyc);
@@ -258,6 +291,8 @@ int main(int argc, char** argv) {
             run<4>(C, steps, work, gbuf, flags, sink, cyc);
             run<5>(C, steps, work, gbuf, flags, sink, cyc);
             run<10>(C, steps, work, gbuf, flags, sink, cyc);
+            run<11>(C, steps, work, gbuf, flags, sink, cyc);
+            run<14>(C, steps, work, gbuf, flags, sink, cyc);
             run<7>(C, steps, work, gbuf, flags, sink, cyc);
             run<8>(C, steps, work, gbuf, flags, sink, cyc);
             run<9>(C, steps, work, gbuf, flags, sink, cyc);

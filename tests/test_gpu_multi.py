@@ -1,0 +1,67 @@
+"""GPU, world_size 2 (skipped on a 1-GPU box): the body-sharded NCCL path and the trajectory
+ensemble over two GPUs give exactly the single-GPU results."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from conftest import ROOT, case_path, golden_lines
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import importlib, os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+nb = importlib.import_module("nthu_ipc_nbody-simulation_b200")
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n, steps = 4096, 6
+s = nb.synthetic_system(n, seed=21)
+sh = nb.ShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
+sh.advance(steps)
+torch.cuda.synchronize()
+q, v = sh.positions(), sh.velocities()
+case = nb.read_input(%(case)r)
+ans, secs, pairs = nb.solve_distributed(case, rank, world, local)
+if rank == 0:
+    q1, v1 = s.q.copy(), s.v.copy()
+    nb.run_steps(0, steps, n, q1, v1, s.m, s.is_device, gpu=local)
+    print(json.dumps(dict(sharded_equal=bool(np.array_equal(q, q1) and np.array_equal(v, v1)),
+                          text=nb.format_output(ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost),
+                          n_traj=ans.n_trajectories)))
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpus_sharded_and_ensemble(nb, tmp_path):
+    if nb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT, case=case_path("b200")))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    import json
+    out = json.loads([l for l in r.stdout.decode().split("\n") if l.startswith("{")][-1])
+    assert out["sharded_equal"]
+    g = golden_lines("b200")
+    a, b, c = out["text"].split("\n")[:3]
+    assert b == str(g["hit_time_step"]) and c == g["text"].split("\n")[2]
+    assert abs(float(a) - g["min_dist"]) <= 1e-6 * g["min_dist"]
+    assert out["n_traj"] == 5
+
+
+def test_solve_over_all_visible_gpus_matches_golden(nb):
+    """nb_solve with one host thread per GPU (hw5.cu:566-567, 587-588 generalised)."""
+    g = nb.device_count()
+    s = nb.read_input(case_path("b80"))
+    gold = golden_lines("b80")
+    ans = nb.solve(s, gpus=g)
+    assert ans.n_gpus_used == min(g, 6) and ans.n_trajectories == 6
+    assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (
+        gold["hit_time_step"], gold["gravity_device_id"], gold["missile_cost"])
+    assert abs(ans.min_dist - gold["min_dist"]) <= 1e-6 * gold["min_dist"]

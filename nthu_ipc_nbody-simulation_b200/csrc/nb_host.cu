@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -423,8 +424,13 @@ int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n
     if (rc) return rc;
     if (!evs || n_parts < 1 || part < 0 || part >= n_parts || n_steps < 0) return NB_ERR_ARG;
     if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
+    const bool verbose = getenv("NB_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
+    auto t_a = now();
     rc = nb::check_gpu(gpu);
     if (rc) return rc;
+    const double s_driver = secs_since(t_a);
     const int T = 2 + (int)devs.size();
     std::vector<int> mine;
     for (int t = part; t < T; t += n_parts) mine.push_back(t);
@@ -432,14 +438,23 @@ int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n
     if (pair_interactions) *pair_interactions = 0;
     if (mine.empty()) return NB_OK;
     DeviceBatch b;
+    auto t_b = now();
     rc = b.init(gpu, (int)mine.size(), sys->n, math);
+    const double s_ctx = secs_since(t_b);
+    auto t_c = now();
     for (size_t s = 0; s < mine.size() && !rc; s++) {
         const int t = mine[s];
         const int kind = t == 0 ? NB_KIND_Q1 : (t == 1 ? NB_KIND_Q2 : NB_KIND_Q3);
         rc = b.set_system((int)s, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid, kind,
                           t >= 2 ? devs[t - 2] : -1, 0);
     }
+    const double s_upload = secs_since(t_c);
+    auto t_d = now();
     if (!rc) rc = b.run(n_steps, true);
+    const double s_run = secs_since(t_d);
+    if (verbose)
+        fprintf(stderr, "nbody_b200: gpu %d part %d/%d: driver init %.3f s, context+alloc %.3f s, upload %.3f s, "
+                        "run %.3f s (kernels %.3f s)\n", gpu, part, n_parts, s_driver, s_ctx, s_upload, s_run, b.gpu_seconds);
     if (!rc)
         for (size_t s = 0; s < mine.size(); s++) evs[mine[s]] = b.h_ev[s];
     if (gpu_seconds) *gpu_seconds = b.gpu_seconds;

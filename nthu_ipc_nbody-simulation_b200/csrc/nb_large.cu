@@ -28,7 +28,7 @@ namespace {
 constexpr int TJ = 256;      // bodies per j tile (8 KiB)
 constexpr int STAGES = 3;    // TMA ring depth
 constexpr int LT = 128;      // threads per block
-constexpr int MAX_JSPLIT = 32;
+constexpr int MAX_JSPLIT = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -198,7 +198,8 @@ int pick_jsplit(int math, int n, int i_count, int ipt) {
     const int iblocks = (i_count + LT * ipt - 1) / (LT * ipt);
     int js = 1;
     // enough equal pieces (>= ~14 per SM) that the 148 SMs finish together, >= 2 tiles per piece;
-    // measured on B200: 65 536 bodies, IPT 4: 1 split 43.8 %, 8 splits 54.6 %, 16 splits 54.9 % of peak
+    // measured on B200: 65 536 bodies, IPT 4: 1 split 43.8 %, 8 splits 54.6 %, 16 splits 54.9 % of peak;
+    // an 8 192-body shard (P = 8) has only 16 i-blocks and needs 128 splits to fill the GPU
     while (js < MAX_JSPLIT && iblocks * js < 14 * 148 && n / (js * 2) >= 2 * TJ) js *= 2;
     return js;
 }
@@ -226,7 +227,10 @@ extern "C" {
 long long nb_large_scratch_bytes(int n, int i_count) {
     (void)n;
     if (i_count < 1) return 0;
-    return (long long)MAX_JSPLIT * 3 * i_count * (long long)sizeof(double);
+    read_env();
+    // the largest split count pick_jsplit can choose for this shard (STRICT uses 1)
+    const int js = g_jsplit > 0 ? g_jsplit : pick_jsplit(NB_MATH_FAST, n, i_count, g_ipt);
+    return (long long)js * 3 * i_count * (long long)sizeof(double);
 }
 
 int nb_large_pack(int math, int n, const double* q_planar_dev, const double* m0_dev, const unsigned char* is_device_dev,

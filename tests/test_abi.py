@@ -98,7 +98,8 @@ def test_argument_validation(nb):
     q = np.zeros(3)
     assert L.nb_run_steps(0, 0, 0, None, None, None, None, 0, 1) == nb.NB_ERR_ARG
     assert L.nb_run_steps(0, 7, 1, nb._d(q), nb._d(q), nb._d(q), nb._u(np.zeros(1, np.uint8)), 0, 1) == nb.NB_ERR_ARG
-    assert L.nb_large_scratch_bytes(65536, 8192) == 32 * 3 * 8192 * 8
+    assert L.nb_large_scratch_bytes(65536, 8192) == 128 * 3 * 8192 * 8  # 16 i-blocks x 128 j-splits fill 148 SMs
+    assert L.nb_large_scratch_bytes(65536, 65536) == 32 * 3 * 65536 * 8
 
 
 def test_compute_without_gpu_fails_loudly(nb):

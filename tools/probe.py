@@ -71,5 +71,17 @@ def solve(case="b200", gpus=1):
           "gpu %.3fs wall %.3fs (call %.3fs) %.3e pairs/s" % (a.gpu_seconds, a.wall_seconds, time.time() - t0, a.pair_interactions / a.gpu_seconds), flush=True)
 
 
+def cli(case="b1024", reps=2):
+    """Process wall time of the hw5 binary (CUDA start-up included)."""
+    import subprocess
+    inp = os.path.join(G, case + ".in")
+    for _ in range(int(reps)):
+        t0 = time.time()
+        r = subprocess.run([nb.HW5_PATH, inp, "/tmp/cli.out"], env=dict(os.environ, NB_VERBOSE="1"), capture_output=True)
+        dt = time.time() - t0
+        ok = open("/tmp/cli.out").read() == open(os.path.join(G, case + ".out")).read()
+        print("hw5 %s: process wall %.3f s, rc %d, byte-identical %s\n%s" % (case, dt, r.returncode, ok, r.stderr.decode().strip()), flush=True)
+
+
 if __name__ == "__main__":
     globals()[sys.argv[1]](*sys.argv[2:])

@@ -298,6 +298,68 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ensemble(args):
+    """BASELINE config 4: 1024 independent 1024-body systems (member k = b1024.in with velocities scaled by
+    1 + 1e-9 k), split over the ranks with no collective; one block per system, one launch."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    nb = importlib.import_module(PKG)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S_total = args.systems
+    base = nb.read_input(os.path.join(CASES, "b1024.in"))
+    mine = list(range(rank, S_total, world))
+    S, n = len(mine), base.n
+    q0 = np.tile(base.q, (S, 1))
+    v0 = np.stack([base.v * (1 + 1e-9 * k) for k in mine])
+    m = np.tile(base.m, (S, 1))
+    isdev = np.tile(base.is_device, (S, 1))
+    pl, ast = [base.planet] * S, [base.asteroid] * S
+
+    def once(steps):
+        q, v = q0.copy(), v0.copy()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ev, secs = nb.ensemble_run(q, v, m, isdev, pl, ast, kind=nb.KIND_Q2, step_end=steps, gpu=local)
+        wall = time.perf_counter() - t0
+        t = torch.tensor([secs, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), ev, q
+
+    once(max(args.warmup, 1))
+    secs, wall, ev, q = once(args.steps)
+    # member 0 of rank 0 is the golden system itself: its state must equal a plain trajectory's
+    ok = True
+    if rank == 0:
+        t = nb.Trajectory(base, nb.KIND_Q2, gpu=local)
+        t.run(args.steps)
+        ok = bool(np.array_equal(t.state()[0], q[0]))
+    pairs = S_total * args.steps * n * (n - 1)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": pairs / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (b1024.in with scaled velocities)",
+            "config": {"workload": "synthetic ensemble of %d independent 1024-body systems" % S_total,
+                       "systems_per_rank": S, "parallelism": "ensemble x%d, no collective" % world,
+                       "kernel": "traj_kernel (one block per system, whole run in one launch)"},
+            "frac_of_fp64_peak": pairs / secs * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
+            "e2e": {"value": pairs / wall, "unit": UNIT, "h2d_bytes_per_step": int(S * n * 57 / args.steps),
+                    "d2h_bytes_per_step": int(S * n * 48 / args.steps), "note": "states uploaded once per launch, not per step"},
+            "member0_equals_single_trajectory": ok, "gpu_launches": 2}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,10 +370,14 @@ def main():
     ap.add_argument("--no-b1024", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--workload", default="large", choices=["large", "ensemble"])
+    ap.add_argument("--systems", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "ensemble":
+        run_ensemble(args)
     else:
         run_ours(args)
 

@@ -5,7 +5,10 @@
 //        in std::scientific at 17 significant digits (== printf "%.16e").
 // Unlike hw5.cu:110-130 the bodies are NOT permuted: planet / asteroid / device indexes are passed
 // to the kernels, so the reported device id needs no back-map (hw5.cu:601).
+#include <unistd.h>
+
 #include <cerrno>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -116,8 +119,31 @@ int nb_write_output(const char* path, double min_dist, int hit_time_step, int gr
     return NB_OK;
 }
 
+// Start-up path: creating a CUDA context costs hundreds of milliseconds per GPU
+// and the driver initialises every VISIBLE device, so before the first CUDA call the process narrows
+// CUDA_VISIBLE_DEVICES to the GPUs that will get a trajectory (2 + number of devices of the input).
+// The GPU count comes from the /dev/nvidiaN nodes (no CUDA or NVML call); a CUDA_VISIBLE_DEVICES set by the user wins.
+static int count_gpus_procfs() {
+    int cnt = 0;  // device nodes /dev/nvidia0, /dev/nvidia1, ... (containers often hide /proc/driver/nvidia/gpus)
+    for (int g = 0; g < 64; g++) {
+        char path[32];
+        snprintf(path, sizeof path, "/dev/nvidia%d", g);
+        if (access(path, F_OK) == 0) cnt++;
+    }
+    return cnt;
+}
+
 // hw5 <input> <output> (hw5.cu:532-616)
 int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
+    const bool verbose = getenv("NB_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (verbose) {
+            auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "nbody_b200: %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+            t0 = t1;
+        }
+    };
     int n, planet, asteroid;
     int rc = nb_read_header(input_path, &n, &planet, &asteroid);
     if (rc) return rc;
@@ -125,19 +151,36 @@ int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
     std::vector<unsigned char> dev(n);
     rc = nb_read_input(input_path, n, &n, &planet, &asteroid, q.data(), v.data(), m.data(), dev.data());
     if (rc) return rc;
+    lap("read input");
+    int n_traj = 2;
+    for (int i = 0; i < n; i++) n_traj += dev[i] ? 1 : 0;
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        const int present = count_gpus_procfs();
+        int want = n_gpus > 0 ? n_gpus : n_traj;
+        if (present > 0 && want < present) {
+            std::string list;
+            for (int g = 0; g < want; g++) list += (g ? "," : "") + std::to_string(g);
+            setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+            if (verbose) fprintf(stderr, "nbody_b200: %d GPUs present, using CUDA_VISIBLE_DEVICES=%s\n", present, list.c_str());
+        }
+    }
     if (n_gpus <= 0) {
         rc = nb_device_count(&n_gpus);
         if (rc) return rc;
     }
+    lap("driver initialisation");
     nb_system sys{n, planet, asteroid, q.data(), v.data(), m.data(), dev.data()};
     nb_answer ans;
     rc = nb_solve(&sys, nullptr, n_gpus, NB_N_STEPS, NB_MATH_FAST, &ans);
     if (rc) return rc;
-    if (getenv("NB_VERBOSE"))
+    lap("three queries (nb_solve)");
+    if (verbose)
         fprintf(stderr, "nbody_b200: %d trajectories on %d GPU(s): gpu %.3f s, solve wall %.3f s, %.3e pairs/s\n",
                 ans.n_trajectories, ans.n_gpus_used, ans.gpu_seconds, ans.wall_seconds,
                 ans.gpu_seconds > 0 ? ans.pair_interactions / ans.gpu_seconds : 0.0);
-    return nb_write_output(output_path, ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost);
+    rc = nb_write_output(output_path, ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost);
+    lap("write output");
+    return rc;
 }
 
 }  // extern "C"

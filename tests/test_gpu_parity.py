@@ -283,6 +283,31 @@ def test_large_path_fast_accelerations(nb, oracle):
     assert np.allclose(v, vo, rtol=1e-12, atol=0)
 
 
+def test_full_size_65536_one_step_against_oracle_and_invariants(nb, oracle):
+    """BASELINE's full size (config C5, 65 536 bodies): one step from rest, so v = a*dt.
+    (1) against the CPU oracle (all host threads, 4.3e9 pairs): every component within 1e-12 of the body's
+        largest component; (2) momentum: sum_i m_i a_i = 0 for exact pairwise forces (Newton's third law) - a
+        checksum over all 4.3e9 pair terms that needs no oracle; (3) linearity: doubling every mass doubles
+        every acceleration bit for bit (power-of-two scaling commutes with every rounding)."""
+    n = 65536
+    s = nb.synthetic_system(n, seed=42)
+    s.v[:] = 0.0
+    s.is_device[:] = 0  # the modulation is covered elsewhere; here G*m is a pure per-body scale
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 1, n, q, v, s.m, s.is_device)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, n, qo, vo, s.m, s.is_device, 0, 1)
+    scale = np.abs(vo.reshape(3, -1)).max(axis=0)
+    assert (np.abs(v - vo).reshape(3, -1) / scale).max() < 1e-12
+    assert np.abs(q - qo).max() <= 2 * np.spacing(np.abs(qo)).max()
+    a = v.reshape(3, n) / 60.0
+    p = (a * s.m).sum(axis=1)
+    assert np.all(np.abs(p) <= 1e-11 * np.abs(a * s.m).sum(axis=1))
+    q2, v2 = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 1, n, q2, v2, 2.0 * s.m, s.is_device)
+    assert np.array_equal(v2, 2.0 * v)
+
+
 def test_sharded_single_rank_matches_host_api(nb):
     """The torch-plumbed device-pointer path (nb_large_pack / nb_large_step) == nb_run_steps."""
     import torch

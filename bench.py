@@ -151,6 +151,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
@@ -169,7 +171,10 @@ def run_ours(args):
 
     n = args.n
     system = nb.synthetic_system(n, seed=42)
-    sh = nb.ShardedSystem(system, rank=rank, world=world, device=dev)
+    if args.exchange == "p2p":
+        sh = nb.P2PShardedSystem(system, rank=rank, world=world, device=dev)
+    else:
+        sh = nb.ShardedSystem(system, rank=rank, world=world, device=dev)
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
@@ -271,6 +276,8 @@ def run_ours(args):
                        else "synthetic %d-body single system, body-sharded" % n,
                        "n_bodies": n, "seed": 42, "bodies_per_rank": sh.i_count, "pairs_per_step": pairs_per_step,
                        "math": "fast (16 FP64 instr/pair)", "parallelism": "body-sharded x%d" % world,
+                       "exchange": ("P2P stores fused into the integrate kernel (peer-mapped buffers, no NCCL on the data path)"
+                                    if args.exchange == "p2p" else "in-place NCCL all-gather of pos4 rows") if world > 1 else "none (1 GPU)",
                        "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB memset, outside the per-step events)",
                        "exchange_bytes_per_rank_per_step": sh.bytes_exchanged_per_step()},
             "frac_of_fp64_peak": value * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
@@ -371,6 +378,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--workload", default="large", choices=["large", "ensemble"])
+    ap.add_argument("--exchange", default=os.environ.get("NB_EXCHANGE", "p2p"), choices=["nccl", "p2p"])
     ap.add_argument("--systems", type=int, default=1024)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

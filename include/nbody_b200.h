@@ -176,6 +176,35 @@ int nb_large_step(int math, int step, int n, int i_begin, int i_count, const dou
                   double* pos4_out_dev, double* vel_dev, const double* m0_dev,
                   const unsigned char* is_device_dev, void* scratch_dev, void* stream);
 
+/* The same step with the exchange fused in (north star (d), "P2P stores overlapped with the local tile"):
+ * the integrate kernel stores every new pos4 row straight into EVERY rank's pos4_out buffer through
+ * peer-mapped pointers (NVLink P2P; entry `rank` is the own buffer); each of its
+ * nb_large_blocks_per_step(i_count) blocks then adds 1, with a system-scope release, to counter
+ * [step & 1][rank] of every rank (a rank's counter block is nb_large_p2p_counter_bytes() bytes, zeroed).
+ * The NEXT step's acceleration kernel waits inside the kernel: blocks whose j range is local start at once
+ * (the grid is rotated so that they run first), the others wait until the counter of exactly the source
+ * rank they read reaches wait_target = blocks * (steps of that parity executed so far); 0 = no wait
+ * (first step).  peer_* are HOST arrays of device pointers (own allocations or nb_ipc_open results);
+ * n must be divisible by world and this rank's shard is [rank*n/world, (rank+1)*n/world).
+ * nb_large_wait_p2p is the stand-alone wait on all sources (before the host reads the final buffer). */
+int nb_large_step_p2p(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev,
+                      double* const* peer_pos4_out, unsigned long long* const* peer_counters, int world,
+                      int rank, unsigned long long wait_target, int* status_dev, double* vel_dev,
+                      const double* m0_dev, const unsigned char* is_device_dev, void* scratch_dev,
+                      void* stream);
+int nb_large_blocks_per_step(int i_count);
+int nb_large_p2p_counter_bytes(void);
+int nb_large_wait_p2p(const unsigned long long* my_counters, int parity, int world,
+                      unsigned long long target, int* status_dev, void* stream);
+/* raw device memory (zero-filled cudaMalloc on the current device) and CUDA IPC handles (64 bytes), so that
+ * one process per GPU can map its peers' exchange buffers */
+int nb_dev_alloc(long long bytes, void** dev_ptr);
+int nb_dev_free(void* dev_ptr);
+int nb_dev_copy(void* dst, const void* src, long long bytes, int kind /*0 H2D, 1 D2H, 2 D2D*/, void* stream);
+int nb_ipc_export(void* dev_ptr, unsigned char* handle64);
+int nb_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int nb_ipc_close(void* dev_ptr);
+
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */
 int nb_fp64_peak(int gpu, double* tflops, double* seconds);

@@ -68,7 +68,8 @@ ABI_SYMBOLS = [
     "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_destroy",
     "nb_ensemble_run", "nb_solve", "nb_solve_trajectory_count", "nb_solve_partial", "nb_solve_combine",
     "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_hw5_main",
-    "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_fp64_peak", "nb_fp64_peak_variant",
+    "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_large_step_p2p", "nb_large_blocks_per_step", "nb_large_p2p_counter_bytes", "nb_large_wait_p2p",
+    "nb_dev_alloc", "nb_dev_free", "nb_dev_copy", "nb_ipc_export", "nb_ipc_open", "nb_ipc_close", "nb_fp64_peak", "nb_fp64_peak_variant",
 ]
 
 _lib_handle = None
@@ -117,6 +118,17 @@ def lib():
     L.nb_large_unpack.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nb_large_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_large_step_p2p.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_large_blocks_per_step.argtypes = [C.c_int]
+    L.nb_large_wait_p2p.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    L.nb_dev_alloc.argtypes = [C.c_longlong, C.POINTER(C.c_void_p)]
+    L.nb_dev_free.argtypes = [C.c_void_p]
+    L.nb_dev_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    L.nb_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.nb_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.nb_ipc_close.argtypes = [C.c_void_p]
     L.nb_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     L.nb_fp64_peak_variant.argtypes = [C.c_int, C.c_int, _dp]
     _lib_handle = L
@@ -350,4 +362,4 @@ def fp64_peak(gpu=0, variant=0):
     return t.value
 
 
-from .sharded import ShardedSystem, partition, synthetic_system  # noqa: E402,F401
+from .sharded import P2PShardedSystem, ShardedSystem, partition, synthetic_system  # noqa: E402,F401

@@ -17,6 +17,7 @@
 // The split exists only to cut the work into enough equal pieces to balance 148 SMs.
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "nb_internal.h"
@@ -59,17 +60,50 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+// P2P exchange only: the rows of source rank r are valid once counters[r] >= target (every block of r's
+// integrate kernel has stored its rows here and released).  Blocks whose j range is local start at once -
+// the grid is rotated so that they are scheduled first - and the others wait for exactly the ranks they
+// read, so the arrival of the remote rows overlaps with the local tiles.
+struct ArrivalWait {
+    const unsigned long long* counters;  // [world] for the parity being read; nullptr = nothing to wait for
+    unsigned long long target;
+    int rows_per_rank, my_rank;
+    int* status;
+};
+
 template <int MATH, int IPT>
 __global__ void __launch_bounds__(LT)
 large_accel_kernel(const double4* __restrict__ pos4, int n, int i_begin, int i_count, int j_per_split,
-                   double* __restrict__ apart) {
+                   double* __restrict__ apart, ArrivalWait aw) {
     __shared__ alignas(128) double4 tile[STAGES][TJ];
     __shared__ alignas(8) uint64_t full[STAGES];
 
     const int tid = threadIdx.x;
-    const int j0 = blockIdx.y * j_per_split;
+    int ysplit = blockIdx.y;
+    if (aw.counters) ysplit = (int)((blockIdx.y + (unsigned)(aw.my_rank * aw.rows_per_rank) / j_per_split) % gridDim.y);
+    const int j0 = ysplit * j_per_split;
     const int j1 = min(n, j0 + j_per_split);
     const int ntiles = (j1 - j0 + TJ - 1) / TJ;
+    if (aw.counters) {
+        if (tid == 0) {
+            const int lo = j0 / aw.rows_per_rank, hi = (j1 - 1) / aw.rows_per_rank;
+            const long long t0 = clock64();
+            for (int src = lo; src <= hi; src++) {
+                if (src == aw.my_rank) continue;
+                for (;;) {
+                    unsigned long long v;
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(aw.counters + src) : "memory");
+                    if (v >= aw.target) break;
+                    if (clock64() - t0 > 20000000000LL) {  // ~10 s: a lost peer must not hang the GPU
+                        *aw.status = 1;
+                        break;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA (async proxy) reads what was just acquired
+        }
+        __syncthreads();
+    }
 
     double xi[IPT], yi[IPT], zi[IPT], ax[IPT], ay[IPT], az[IPT];
     int il[IPT];
@@ -120,7 +154,7 @@ large_accel_kernel(const double4* __restrict__ pos4, int n, int i_begin, int i_c
         if (tid == 0 && t + STAGES < ntiles) issue(t + STAGES);
     }
 
-    double* out = apart + (size_t)blockIdx.y * 3 * i_count;
+    double* out = apart + (size_t)ysplit * 3 * i_count;
 #pragma unroll
     for (int k = 0; k < IPT; k++)
         if (il[k] < i_count) {
@@ -153,6 +187,66 @@ __global__ void large_integrate_kernel(const double4* __restrict__ pos4, double4
     kick_drift(a[2], vz, z);
     vel[il] = vx, vel[il + i_count] = vy, vel[il + 2 * i_count] = vz;
     pos4_out[i] = make_double4(x, y, z, gm_eff(m0[i], is_device[i] != 0, fst_next));
+}
+
+// The exchange fused into the integrate step (north star (d), second option): the new pos4 record of every
+// local body is stored straight into EVERY rank's pos4_out buffer (peer-mapped pointers, NVLink P2P stores;
+// the own buffer is peer `rank`), then each block raises every rank's arrival counter of this step's parity
+// with a system-scope release.  No NCCL call, no staging copy: the all-gather is these stores.
+constexpr int MAX_PEERS = 16;
+struct PeerSet {
+    double4* pos4_out[MAX_PEERS];
+    unsigned long long* counter[MAX_PEERS];  // per rank: [2 parities][MAX_PEERS source ranks]
+    int world, my_rank;
+};
+
+__global__ void large_integrate_push_kernel(const double4* __restrict__ pos4, PeerSet peers,
+                                            double* __restrict__ vel, const double* __restrict__ m0,
+                                            const unsigned char* __restrict__ is_device,
+                                            const double* __restrict__ apart, int jsplit, int i_begin, int i_count,
+                                            double fst_next, int parity) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il < i_count) {
+        double a[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double s = apart[(size_t)c * i_count + il];
+            for (int k = 1; k < jsplit; k++) s += apart[((size_t)k * 3 + c) * i_count + il];
+            a[c] = s;
+        }
+        const int i = i_begin + il;
+        const double4 p = pos4[i];
+        double x = p.x, y = p.y, z = p.z;
+        double vx = vel[il], vy = vel[il + i_count], vz = vel[il + 2 * i_count];
+        kick_drift(a[0], vx, x);
+        kick_drift(a[1], vy, y);
+        kick_drift(a[2], vz, z);
+        vel[il] = vx, vel[il + i_count] = vy, vel[il + 2 * i_count] = vz;
+        const double4 rec = make_double4(x, y, z, gm_eff(m0[i], is_device[i] != 0, fst_next));
+        for (int pr = 0; pr < peers.world; pr++) peers.pos4_out[pr][i] = rec;  // coalesced 32 B per lane, per peer
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < peers.world) {
+        unsigned long long* ctr = peers.counter[threadIdx.x] + parity * MAX_PEERS + peers.my_rank;
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ULL) : "memory");
+    }
+}
+
+// device-side wait, in stream order, until this rank's counter says that every block of every rank has
+// delivered its rows (bounded spin: a lost peer raises *status instead of hanging the GPU)
+__global__ void large_wait_kernel(const unsigned long long* counters, unsigned long long target, int* status) {
+    const unsigned long long* counter = counters + threadIdx.x;  // one thread per source rank
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s
+            *status = 1;
+            break;
+        }
+    }
 }
 
 __global__ void large_pack_kernel(int n, const double* __restrict__ q, const double* __restrict__ m0,
@@ -206,11 +300,11 @@ int pick_jsplit(int math, int n, int i_count, int ipt) {
 
 template <int MATH>
 int launch_accel(int ipt, dim3 grid, cudaStream_t st, const double4* pos4, int n, int i_begin, int i_count, int jps,
-                 double* apart) {
+                 double* apart, const ArrivalWait& aw) {
     switch (ipt) {
-        case 1: large_accel_kernel<MATH, 1><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
-        case 2: large_accel_kernel<MATH, 2><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
-        default: large_accel_kernel<MATH, 4><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart); break;
+        case 1: large_accel_kernel<MATH, 1><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart, aw); break;
+        case 2: large_accel_kernel<MATH, 2><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart, aw); break;
+        default: large_accel_kernel<MATH, 4><<<grid, LT, 0, st>>>(pos4, n, i_begin, i_count, jps, apart, aw); break;
     }
     count_launch();
     NB_CUDA(cudaGetLastError());
@@ -253,11 +347,11 @@ int nb_large_unpack(int n, const double* pos4_dev, double* q_planar_dev, void* s
     return NB_OK;
 }
 
-int nb_large_step(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev, double* pos4_out_dev,
-                  double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* scratch_dev,
-                  void* stream) {
+static int large_step_impl(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev,
+                           double* pos4_out_dev, const PeerSet* peers, const ArrivalWait& aw, double* vel_dev,
+                           const double* m0_dev, const unsigned char* is_device_dev, void* scratch_dev, void* stream) {
     if (n < 1 || i_begin < 0 || i_count < 1 || i_begin + i_count > n || step < 1) return NB_ERR_ARG;
-    if (!pos4_dev || !pos4_out_dev || !vel_dev || !m0_dev || !is_device_dev || !scratch_dev) return NB_ERR_ARG;
+    if (!pos4_dev || (!pos4_out_dev && !peers) || !vel_dev || !m0_dev || !is_device_dev || !scratch_dev) return NB_ERR_ARG;
     if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
     read_env();
     const int ipt = g_ipt;
@@ -275,21 +369,110 @@ int nb_large_step(int math, int step, int n, int i_begin, int i_count, const dou
     }
     int rc = math == NB_MATH_STRICT
                  ? launch_accel<MATH_STRICT>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
-                                             (double*)scratch_dev)
+                                             (double*)scratch_dev, aw)
                  : launch_accel<MATH_FAST>(ipt, grid, st, (const double4*)pos4_dev, n, i_begin, i_count, jps,
-                                           (double*)scratch_dev);
+                                           (double*)scratch_dev, aw);
     if (rc) return rc;
     if (g_prof.on) {
         NB_CUDA(cudaEventRecord(pe1, st));
         g_prof.evs.emplace_back(pe0, pe1);
     }
     const double fst_next = fst_table_host(step + 2)[step + 1];
-    large_integrate_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, (double4*)pos4_out_dev,
-                                                                  vel_dev, m0_dev, is_device_dev,
-                                                                  (const double*)scratch_dev, nsplit, i_begin, i_count,
-                                                                  fst_next, math == NB_MATH_STRICT);
+    if (peers)
+        large_integrate_push_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, *peers, vel_dev, m0_dev,
+                                                                       is_device_dev, (const double*)scratch_dev, nsplit,
+                                                                       i_begin, i_count, fst_next, step & 1);
+    else
+        large_integrate_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, (double4*)pos4_out_dev,
+                                                                      vel_dev, m0_dev, is_device_dev,
+                                                                      (const double*)scratch_dev, nsplit, i_begin, i_count,
+                                                                      fst_next, math == NB_MATH_STRICT);
     count_launch();
     NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+int nb_large_step(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev, double* pos4_out_dev,
+                  double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* scratch_dev,
+                  void* stream) {
+    return large_step_impl(math, step, n, i_begin, i_count, pos4_dev, pos4_out_dev, nullptr, ArrivalWait{}, vel_dev,
+                           m0_dev, is_device_dev, scratch_dev, stream);
+}
+
+int nb_large_step_p2p(int math, int step, int n, int i_begin, int i_count, const double* pos4_dev,
+                      double* const* peer_pos4_out, unsigned long long* const* peer_counters, int world, int rank,
+                      unsigned long long wait_target, int* status_dev, double* vel_dev, const double* m0_dev,
+                      const unsigned char* is_device_dev, void* scratch_dev, void* stream) {
+    if (!peer_pos4_out || !peer_counters || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return NB_ERR_ARG;
+    if (n % world != 0 || i_count != n / world || i_begin != rank * i_count || !status_dev) return NB_ERR_ARG;
+    PeerSet ps;
+    ps.world = world;
+    ps.my_rank = rank;
+    ArrivalWait aw{};
+    if (wait_target > 0 && world > 1) {  // rows of step-1 live in the buffer being read; their counters have parity (step-1)&1
+        aw.counters = peer_counters[rank] + ((step - 1) & 1) * MAX_PEERS;
+        aw.target = wait_target;
+        aw.rows_per_rank = i_count;
+        aw.my_rank = rank;
+        aw.status = status_dev;
+    }
+    for (int p = 0; p < world; p++) {
+        if (!peer_pos4_out[p] || !peer_counters[p]) return NB_ERR_ARG;
+        ps.pos4_out[p] = (double4*)peer_pos4_out[p];
+        ps.counter[p] = peer_counters[p];
+    }
+    return large_step_impl(math, step, n, i_begin, i_count, pos4_dev, nullptr, &ps, aw, vel_dev, m0_dev, is_device_dev,
+                           scratch_dev, stream);
+}
+
+int nb_large_blocks_per_step(int i_count) { return i_count < 1 ? 0 : (i_count + 127) / 128; }
+
+int nb_large_p2p_counter_bytes(void) { return 2 * MAX_PEERS * (int)sizeof(unsigned long long); }
+
+int nb_large_wait_p2p(const unsigned long long* my_counters, int parity, int world, unsigned long long target,
+                      int* status_dev, void* stream) {
+    if (!my_counters || !status_dev || world < 1 || world > MAX_PEERS || parity < 0 || parity > 1) return NB_ERR_ARG;
+    large_wait_kernel<<<1, world, 0, (cudaStream_t)stream>>>(my_counters + parity * MAX_PEERS, target, status_dev);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+// ---- raw device memory + CUDA IPC, for the peer-mapped buffers of the P2P exchange (one process per GPU) ----
+int nb_dev_alloc(long long bytes, void** dev_ptr) {
+    if (bytes < 1 || !dev_ptr) return NB_ERR_ARG;
+    NB_CUDA(cudaMalloc(dev_ptr, (size_t)bytes));
+    NB_CUDA(cudaMemset(*dev_ptr, 0, (size_t)bytes));
+    return NB_OK;
+}
+int nb_dev_free(void* dev_ptr) {
+    NB_CUDA(cudaFree(dev_ptr));
+    return NB_OK;
+}
+int nb_dev_copy(void* dst, const void* src, long long bytes, int kind, void* stream) {
+    if (!dst || !src || bytes < 0 || kind < 0 || kind > 2) return NB_ERR_ARG;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    NB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+    NB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return NB_OK;
+}
+int nb_ipc_export(void* dev_ptr, unsigned char* handle64) {
+    if (!dev_ptr || !handle64) return NB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    NB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return NB_OK;
+}
+int nb_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return NB_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    NB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return NB_OK;
+}
+int nb_ipc_close(void* dev_ptr) {
+    NB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
     return NB_OK;
 }
 

@@ -86,6 +86,150 @@ def _cuda_local_step(math):
     return step_fn
 
 
+class P2PShardedSystem:
+    """Body-sharded driver whose exchange is fused into the integrate kernel (north star (d), "P2P stores"):
+    every rank stores its new pos4 rows straight into every rank's buffer over NVLink (peer-mapped CUDA IPC
+    pointers) and signals per-parity arrival counters; a device-side wait precedes the next step's reads.
+    No NCCL call on the data path: torch.distributed only carries the 64-byte IPC handles once."""
+
+    def __init__(self, system, rank=0, world=1, device=None, math=0, group=None, step0=0):
+        import ctypes as C
+
+        import torch
+
+        from . import _check, lib
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("P2PShardedSystem needs a CUDA device (no CPU fallback)")
+        self.torch, self.C, self.L = torch, C, lib()
+        L = self.L
+        self.n, self.rank, self.world, self.group, self.math = system.n, rank, world, group, math
+        self.i_begin, self.i_count = partition(system.n, world, rank)
+        self.step = self.step0 = step0
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        n, ib, ic = self.n, self.i_begin, self.i_count
+        self.m0 = torch.from_numpy(system.m.copy()).to(self.device)
+        self.isdev = torch.from_numpy(system.is_device.copy()).to(self.device)
+        self.vel = torch.from_numpy(system.v.reshape(3, n)[:, ib:ib + ic].copy()).to(self.device).contiguous()
+        self.scratch = torch.empty(int(L.nb_large_scratch_bytes(n, ic)), dtype=torch.uint8, device=self.device)
+        self.blocks = int(L.nb_large_blocks_per_step(ic))
+        # own exchange buffers: pos4[2] and {counter[2], status}
+        self.own = []
+        self.ctr_bytes = int(L.nb_large_p2p_counter_bytes())
+        for nbytes in (32 * n, 32 * n, self.ctr_bytes + 64):
+            ptr = C.c_void_p()
+            _check(L.nb_dev_alloc(nbytes, C.byref(ptr)))
+            self.own.append(ptr.value)
+        self.opened = []
+        peers = [list(self.own)]
+        if world > 1:
+            import torch.distributed as dist
+
+            handles = []
+            for ptr in self.own:
+                h = C.create_string_buffer(64)
+                _check(L.nb_ipc_export(C.c_void_p(ptr), h))
+                handles.append(h.raw)
+            allh = [None] * world
+            dist.all_gather_object(allh, handles, group=group)
+            peers = []
+            for r in range(world):
+                if r == rank:
+                    peers.append(list(self.own))
+                    continue
+                ptrs = []
+                for raw in allh[r]:
+                    ptr = C.c_void_p()
+                    _check(L.nb_ipc_open(raw, C.byref(ptr)))
+                    ptrs.append(ptr.value)
+                    self.opened.append(ptr.value)
+                peers.append(ptrs)
+        vp = C.c_void_p * world
+        self.peer_pos = [vp(*[peers[r][b] for r in range(world)]) for b in range(2)]
+        self.peer_ctr = vp(*[peers[r][2] for r in range(world)])
+        self.cnt = [0, 0]  # steps executed per parity
+        self.cur = 0
+        qd = torch.from_numpy(system.q.copy()).to(self.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _check(L.nb_large_pack(math, n, C.c_void_p(qd.data_ptr()), C.c_void_p(self.m0.data_ptr()),
+                               C.c_void_p(self.isdev.data_ptr()), self.step + 1, C.c_void_p(self.own[0]), C.c_void_p(st)))
+        torch.cuda.current_stream().synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=group)  # every peer has mapped every buffer before the first remote store
+
+    def bytes_exchanged_per_step(self):
+        return 0 if self.world == 1 else 32 * self.i_count * (self.world - 1)
+
+    def _wait_for(self, written_step):
+        """Enqueue the device-side wait for the rows of `written_step` (all ranks, all blocks)."""
+        from . import _check
+
+        C = self.C
+        par = written_step & 1
+        target = self.blocks * self.cnt[par]
+        st = self.torch.cuda.current_stream().cuda_stream
+        _check(self.L.nb_large_wait_p2p(C.c_void_p(self.own[2]), par, self.world, target,
+                                        C.c_void_p(self.own[2] + self.ctr_bytes), C.c_void_p(st)))
+
+    def advance(self, steps=1):
+        from . import _check
+
+        C, L, torch = self.C, self.L, self.torch
+        for _ in range(steps):
+            self.step += 1
+            # rows of step-1 are awaited INSIDE the acceleration kernel, per source rank (0 = first step: packed locally)
+            wait_target = self.blocks * self.cnt[(self.step - 1) & 1] if self.step - 1 > self.step0 else 0
+            st = torch.cuda.current_stream().cuda_stream
+            _check(L.nb_large_step_p2p(self.math, self.step, self.n, self.i_begin, self.i_count,
+                                       C.c_void_p(self.own[self.cur]), self.peer_pos[self.cur ^ 1], self.peer_ctr,
+                                       self.world, self.rank, wait_target, C.c_void_p(self.own[2] + self.ctr_bytes),
+                                       C.c_void_p(self.vel.data_ptr()), C.c_void_p(self.m0.data_ptr()),
+                                       C.c_void_p(self.isdev.data_ptr()), C.c_void_p(self.scratch.data_ptr()), C.c_void_p(st)))
+            self.cnt[self.step & 1] += 1
+            self.cur ^= 1
+
+    def positions(self):
+        """Planar q[3n] of all bodies (host numpy); waits for the last step's rows of every rank."""
+        from . import _check
+
+        C, torch = self.C, self.torch
+        if self.step > self.step0:
+            self._wait_for(self.step)
+        st = torch.cuda.current_stream().cuda_stream
+        p = np.empty((self.n, 4))
+        _check(self.L.nb_dev_copy(p.ctypes.data_as(C.c_void_p), C.c_void_p(self.own[self.cur]), p.nbytes, 1, C.c_void_p(st)))
+        status = np.zeros(1, dtype=np.int32)
+        _check(self.L.nb_dev_copy(status.ctypes.data_as(C.c_void_p), C.c_void_p(self.own[2] + self.ctr_bytes), 4, 1, C.c_void_p(st)))
+        if status[0] != 0:
+            raise RuntimeError("P2P exchange: a peer's rows did not arrive (wait timed out)")
+        return np.ascontiguousarray(p[:, :3].T).reshape(-1)
+
+    def velocities(self):
+        torch = self.torch
+        if self.world == 1:
+            return self.vel.detach().to("cpu").numpy().reshape(-1).copy()
+        import torch.distributed as dist
+
+        parts = [torch.empty_like(self.vel) for _ in range(self.world)]
+        dist.all_gather(parts, self.vel, group=self.group)
+        return np.concatenate([p.to("cpu").numpy() for p in parts], axis=1).reshape(-1)
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to go
+        for ptr in self.opened:
+            self.L.nb_ipc_close(self.C.c_void_p(ptr))
+        for ptr in self.own:
+            self.L.nb_dev_free(self.C.c_void_p(ptr))
+        self.opened, self.own = [], []
+
+
 class ShardedSystem:
     def __init__(self, system, rank=0, world=1, device=None, math=0, group=None, local_step=None, step0=0):
         import torch

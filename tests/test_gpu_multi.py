@@ -24,12 +24,17 @@ sh = nb.ShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
 sh.advance(steps)
 torch.cuda.synchronize()
 q, v = sh.positions(), sh.velocities()
+pp = nb.P2PShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
+pp.advance(steps)
+qp, vp = pp.positions(), pp.velocities()
+pp.close()
+p2p_equal = bool(np.array_equal(q, qp) and np.array_equal(v, vp))
 case = nb.read_input(%(case)r)
 ans, secs, pairs = nb.solve_distributed(case, rank, world, local)
 if rank == 0:
     q1, v1 = s.q.copy(), s.v.copy()
     nb.run_steps(0, steps, n, q1, v1, s.m, s.is_device, gpu=local)
-    print(json.dumps(dict(sharded_equal=bool(np.array_equal(q, q1) and np.array_equal(v, v1)),
+    print(json.dumps(dict(p2p_equal=p2p_equal, sharded_equal=bool(np.array_equal(q, q1) and np.array_equal(v, v1)),
                           text=nb.format_output(ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost),
                           n_traj=ans.n_trajectories)))
 dist.destroy_process_group()
@@ -48,6 +53,7 @@ def test_two_gpus_sharded_and_ensemble(nb, tmp_path):
     import json
     out = json.loads([l for l in r.stdout.decode().split("\n") if l.startswith("{")][-1])
     assert out["sharded_equal"]
+    assert out["p2p_equal"]  # P2P-store exchange == NCCL all-gather exchange, bit for bit
     g = golden_lines("b200")
     a, b, c = out["text"].split("\n")[:3]
     assert b == str(g["hit_time_step"]) and c == g["text"].split("\n")[2]

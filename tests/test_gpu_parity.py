@@ -322,6 +322,22 @@ def test_sharded_single_rank_matches_host_api(nb):
     assert np.array_equal(sh.positions(), q) and np.array_equal(sh.velocities(), v)
 
 
+def test_p2p_fused_exchange_single_rank(nb):
+    """The integrate kernel that stores the new rows into the peers' buffers (here: only its own) and the
+    counter / device-side wait protocol give the NCCL path's result bit for bit."""
+    import torch
+
+    n = 4096
+    s = nb.synthetic_system(n, seed=11)
+    a = nb.ShardedSystem(s, device="cuda:0")
+    b = nb.P2PShardedSystem(s, device="cuda:0")
+    a.advance(7)
+    b.advance(7)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.positions(), b.positions()) and np.array_equal(a.velocities(), b.velocities())
+    b.close()
+
+
 def test_two_shards_on_one_gpu_equal_one_shard(nb):
     """Body sharding is exact: integrating [0, n/2) and [n/2, n) separately against all bodies and
     exchanging pos4 rows gives the unsharded result bit for bit (the all-gather is emulated by a copy)."""

@@ -140,8 +140,16 @@ large_accel_kernel(const double4* __restrict__ pos4, int n, int i_begin, int i_c
 #pragma unroll 4
             for (int j = 0; j < TJ; j++) {
                 const double4 b = tj[j];
+                if (MATH == MATH_FAST) {
+                    double c[IPT], dx[IPT], dy[IPT], dz[IPT];
 #pragma unroll
-                for (int k = 0; k < IPT; k++) pair<MATH>(xi[k], yi[k], zi[k], b.x, b.y, b.z, b.w, ax[k], ay[k], az[k]);
+                    for (int k = 0; k < IPT; k++) pair_coeff_fast(xi[k], yi[k], zi[k], b.x, b.y, b.z, b.w, c[k], dx[k], dy[k], dz[k]);
+#pragma unroll
+                    for (int k = 0; k < IPT; k++) pair_accum_fast(c[k], dx[k], dy[k], dz[k], ax[k], ay[k], az[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < IPT; k++) pair<MATH>(xi[k], yi[k], zi[k], b.x, b.y, b.z, b.w, ax[k], ay[k], az[k]);
+                }
             }
         } else {
             for (int j = 0; j < cnt; j++) {

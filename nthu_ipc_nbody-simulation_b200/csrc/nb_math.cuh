@@ -67,13 +67,30 @@ __device__ __forceinline__ void pair(double xi, double yi, double zi, double xj,
         double c = (gmj * y0) * (y2 * p);
         // The three accumulates share the multiplicand c.  A DFMA that reads three distinct register
         // pairs costs 3 pipe cycles instead of 2 on B200 (measured: nb_fp64_peak_variant 1 = 24.8 of
-        // 37.1 TFLOP/s); keeping the triple adjacent lets ptxas mark c ".reuse" for the 2nd and 3rd.
-        asm("fma.rn.f64 %0, %3, %4, %0;\n\t"
-            "fma.rn.f64 %1, %3, %5, %1;\n\t"
-            "fma.rn.f64 %2, %3, %6, %2;"
-            : "+d"(ax), "+d"(ay), "+d"(az)
-            : "d"(c), "d"(dx), "d"(dy), "d"(dz));
+        // 37.1 TFLOP/s); when ptxas keeps the triple adjacent it marks c ".reuse" for the 2nd and 3rd.
+        ax = fma(c, dx, ax);
+        ay = fma(c, dy, ay);
+        az = fma(c, dz, az);
     }
+}
+
+// FAST pair term split in two, so that a kernel can first compute the coefficients of several pairs and then
+// issue all their accumulate DFMAs back to back (three per pair, sharing the multiplicand c: see pair<>).
+__device__ __forceinline__ void pair_coeff_fast(double xi, double yi, double zi, double xj, double yj, double zj,
+                                                double gmj, double& c, double& dx, double& dy, double& dz) {
+    dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const double r2 = fma(dx, dx, fma(dy, dy, fma(dz, dz, EPS2)));
+    const double y0 = rsqrt_seed(r2);
+    const double y2 = y0 * y0;
+    const double e = fma(-r2, y2, 1.0);
+    const double p = fma(e, fma(e, 1.875, 1.5), 1.0);
+    c = (gmj * y0) * (y2 * p);
+}
+__device__ __forceinline__ void pair_accum_fast(double c, double dx, double dy, double dz, double& ax, double& ay,
+                                                double& az) {
+    ax = fma(c, dx, ax);
+    ay = fma(c, dy, ay);
+    az = fma(c, dz, az);
 }
 
 // v += a*dt; q += v*dt (nbody.cc:77-88, hw5.cu:235-236).  O(n) per step, so both math modes keep

@@ -121,6 +121,8 @@ int nb_traj_run(nb_traj* t, int step_end, nb_events* ev);
 int nb_traj_state(nb_traj* t, double* q, double* v, double* m, int* step);
 /* fork: a new trajectory of `kind` starting from t's current state (hw5.cu:275-284 snapshot, :482-483 restore) */
 int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out);
+/* the same onto another GPU: q, v travel device to device (peer copy), never through the host */
+int nb_traj_fork_on(nb_traj* t, int gpu, int kind, int destroy_device, nb_traj** out);
 int nb_traj_destroy(nb_traj* t);
 
 /* ---- ensembles ------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ class NbAnswer(C.Structure):
 # every symbol include/nbody_b200.h declares (tests/test_abi.py checks the two lists agree)
 ABI_SYMBOLS = [
     "nb_version", "nb_strerror", "nb_last_error_detail", "nb_device_count", "nb_kernel_launches",
-    "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_destroy",
+    "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_fork_on", "nb_traj_destroy",
     "nb_ensemble_run", "nb_solve", "nb_solve_trajectory_count", "nb_solve_partial", "nb_solve_combine",
     "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_hw5_main",
     "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_large_step_p2p", "nb_large_blocks_per_step", "nb_large_p2p_counter_bytes", "nb_large_wait_p2p",
@@ -98,6 +98,7 @@ def lib():
     L.nb_traj_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(NbEvents)]
     L.nb_traj_state.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
     L.nb_traj_fork.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.nb_traj_fork_on.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.nb_traj_destroy.argtypes = [C.c_void_p]
     L.nb_ensemble_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _up, _ip, _ip, _ip,
                                   C.c_int, C.c_int, C.POINTER(NbEvents), _dp]
@@ -244,9 +245,12 @@ class Trajectory:
         _check(lib().nb_traj_state(self._h, _d(q), _d(v), _d(m), C.byref(step)))
         return q, v, m, step.value
 
-    def fork(self, kind, destroy_device=-1):
+    def fork(self, kind, destroy_device=-1, gpu=None):
         h = C.c_void_p()
-        _check(lib().nb_traj_fork(self._h, kind, destroy_device, C.byref(h)))
+        if gpu is None:
+            _check(lib().nb_traj_fork(self._h, kind, destroy_device, C.byref(h)))
+        else:
+            _check(lib().nb_traj_fork_on(self._h, gpu, kind, destroy_device, C.byref(h)))
         t = Trajectory(None, kind, _handle=h)
         t.n = self.n
         return t

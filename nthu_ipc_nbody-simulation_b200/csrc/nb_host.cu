@@ -159,8 +159,9 @@ struct DeviceBatch {
             }
         if ((int)di.size() > NB_MAX_DEVICES) return NB_ERR_UNSUPPORTED;
         NB_CUDA(cudaSetDevice(gpu));
-        NB_CUDA(cudaMemcpyAsync(q + (size_t)s * 3 * n, hq, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        NB_CUDA(cudaMemcpyAsync(v + (size_t)s * 3 * n, hv, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        // hq / hv may be null: the caller fills q, v device-to-device afterwards (nb_traj_fork)
+        if (hq) NB_CUDA(cudaMemcpyAsync(q + (size_t)s * 3 * n, hq, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (hv) NB_CUDA(cudaMemcpyAsync(v + (size_t)s * 3 * n, hv, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
         NB_CUDA(cudaMemcpyAsync(m + (size_t)s * n, mm.data(), n * sizeof(double), cudaMemcpyHostToDevice, stream));
         NB_CUDA(cudaMemcpyAsync(isdev + (size_t)s * n, hdev, n, cudaMemcpyHostToDevice, stream));
         if (!di.empty())
@@ -310,19 +311,38 @@ int nb_traj_state(nb_traj* t, double* q, double* v, double* m, int* step) {
     return t->b.get_state(0, q, v, m);
 }
 
-int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out) {
+// Fork = the reference's snapshot + restore (hw5.cu:275-284, 411-413, 482-483) without the host bounce: positions
+// and velocities go device to device (cudaMemcpyPeerAsync over NVLink when the fork lives on another GPU); only the
+// n base masses (Q1 zeroing, device list) pass through the host.
+int nb_traj_fork_on(nb_traj* t, int gpu, int kind, int destroy_device, nb_traj** out) {
     if (!t || !out) return NB_ERR_ARG;
+    if (kind < NB_KIND_PLAIN || kind > NB_KIND_Q3) return NB_ERR_ARG;
+    int rc = nb::check_gpu(gpu);
+    if (rc) return rc;
     const int n = t->b.n;
-    std::vector<double> q(3 * n), v(3 * n), m(n);
-    int rc = t->b.get_state(0, q.data(), v.data(), m.data());
+    std::vector<double> m(n);
+    rc = t->b.get_state(0, nullptr, nullptr, m.data());
     if (rc) return rc;
     nb_traj* f = new nb_traj();
     f->planet = t->planet, f->asteroid = t->asteroid, f->kind = kind, f->destroy_device = destroy_device;
     f->isdev = t->isdev;
-    rc = f->b.init(t->b.gpu, 1, n, t->b.math);
+    rc = f->b.init(gpu, 1, n, t->b.math);
     if (!rc)
-        rc = f->b.set_system(0, q.data(), v.data(), m.data(), f->isdev.data(), f->planet, f->asteroid, kind,
-                             destroy_device, t->b.cur_step[0]);
+        rc = f->b.set_system(0, nullptr, nullptr, m.data(), f->isdev.data(), f->planet, f->asteroid, kind, destroy_device,
+                             t->b.cur_step[0]);
+    if (!rc) {
+        const size_t bytes = 3 * (size_t)n * sizeof(double);
+        cudaError_t e = cudaSuccess;
+        if (gpu == t->b.gpu) {
+            e = cudaMemcpyAsync(f->b.q, t->b.q, bytes, cudaMemcpyDeviceToDevice, f->b.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(f->b.v, t->b.v, bytes, cudaMemcpyDeviceToDevice, f->b.stream);
+        } else {
+            e = cudaMemcpyPeerAsync(f->b.q, gpu, t->b.q, t->b.gpu, bytes, f->b.stream);
+            if (e == cudaSuccess) e = cudaMemcpyPeerAsync(f->b.v, gpu, t->b.v, t->b.gpu, bytes, f->b.stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(f->b.stream);
+        if (e != cudaSuccess) rc = nb::cuda_fail(e, "fork copy", __FILE__, __LINE__);
+    }
     if (rc) {
         f->b.release();
         delete f;
@@ -330,6 +350,11 @@ int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out) {
     }
     *out = f;
     return NB_OK;
+}
+
+int nb_traj_fork(nb_traj* t, int kind, int destroy_device, nb_traj** out) {
+    if (!t) return NB_ERR_ARG;
+    return nb_traj_fork_on(t, t->b.gpu, kind, destroy_device, out);
 }
 
 int nb_traj_destroy(nb_traj* t) {

@@ -176,7 +176,7 @@ large_accel_kernel(const double4* __restrict__ pos4, int n, int i_begin, int i_c
 __global__ void large_integrate_kernel(const double4* __restrict__ pos4, double4* __restrict__ pos4_out,
                                        double* __restrict__ vel, const double* __restrict__ m0,
                                        const unsigned char* __restrict__ is_device, const double* __restrict__ apart,
-                                       int jsplit, int i_begin, int i_count, double fst_next, int strict) {
+                                       int jsplit, int i_begin, int i_count, double fst_next) {
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= i_count) return;
     double a[3];
@@ -394,7 +394,7 @@ static int large_step_impl(int math, int step, int n, int i_begin, int i_count, 
         large_integrate_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, (double4*)pos4_out_dev,
                                                                       vel_dev, m0_dev, is_device_dev,
                                                                       (const double*)scratch_dev, nsplit, i_begin, i_count,
-                                                                      fst_next, math == NB_MATH_STRICT);
+                                                                      fst_next);
     count_launch();
     NB_CUDA(cudaGetLastError());
     return NB_OK;

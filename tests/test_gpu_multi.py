@@ -71,3 +71,23 @@ def test_solve_over_all_visible_gpus_matches_golden(nb):
     assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (
         gold["hit_time_step"], gold["gravity_device_id"], gold["missile_cost"])
     assert abs(ans.min_dist - gold["min_dist"]) <= 1e-6 * gold["min_dist"]
+
+
+def test_fork_onto_another_gpu(nb):
+    """hw5.cu:411-413, 482-483 moves the Q3 fork points GPU1 -> host -> GPU0/1; here the fork is a peer copy."""
+    if nb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = nb.read_input(case_path("b50"))
+    a = nb.Trajectory(s, nb.KIND_Q2, gpu=0)
+    ea = a.run(nb.N_STEPS)
+    r = ea.reach_step[0]
+    c = nb.Trajectory(s, nb.KIND_Q2, gpu=0)
+    c.run(r)
+    f = c.fork(nb.KIND_Q3, 48, gpu=1)
+    ef = f.run(nb.N_STEPS)
+    assert (ef.hit_step, ef.destroyed_step, ef.cost) == (-2, r, 5.23324e9)
+    d = nb.Trajectory(s, nb.KIND_Q3, 48, gpu=0)
+    d.run(nb.N_STEPS)
+    assert all(np.array_equal(x, y) for x, y in zip(f.state()[:2], d.state()[:2]))
+    for t in (a, c, d, f):
+        t.close()

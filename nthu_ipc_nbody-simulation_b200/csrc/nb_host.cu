@@ -42,30 +42,34 @@ struct FstDev {
 };
 static FstDev g_fst_dev[64];
 
-const double* fst_table_host(int min_len) {
-    std::lock_guard<std::mutex> lk(g_fst_mu);
+// grows the host table to at least min_len entries; call with g_fst_mu held
+static void fst_grow_locked(int min_len) {
     if ((int)g_fst_host.size() < min_len) {
-        int len = min_len < NB_N_STEPS + 1 ? NB_N_STEPS + 1 : min_len;
-        // grow without moving entries other threads may be reading: reserve generously once
+        int len = min_len < NB_N_STEPS + 2 ? NB_N_STEPS + 2 : min_len;
         std::vector<double> t(len);
         for (int s = 0; s < len; s++) t[s] = fabs(sin((s * NB_DT) / 6000));
         g_fst_host.swap(t);
     }
-    return g_fst_host.data();
+}
+
+// one entry, by value: safe against a concurrent growth of the table by another host thread
+double fst_value(int step) {
+    std::lock_guard<std::mutex> lk(g_fst_mu);
+    fst_grow_locked(step + 1);
+    return g_fst_host[step];
 }
 
 int fst_table(int gpu, int min_len, const double** out) {
     if (gpu < 0 || gpu >= 64) return NB_ERR_ARG;
-    const double* h = fst_table_host(min_len);
     std::lock_guard<std::mutex> lk(g_fst_mu);
+    fst_grow_locked(min_len);
     FstDev& d = g_fst_dev[gpu];
     if (d.len < min_len) {
-        int len = (int)g_fst_host.size();
-        h = g_fst_host.data();
+        const int len = (int)g_fst_host.size();
         double* p = nullptr;
         NB_CUDA(cudaSetDevice(gpu));
         NB_CUDA(cudaMalloc(&p, (size_t)len * sizeof(double)));
-        NB_CUDA(cudaMemcpy(p, h, (size_t)len * sizeof(double), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaMemcpy(p, g_fst_host.data(), (size_t)len * sizeof(double), cudaMemcpyHostToDevice));
         // the old table (if any) is leaked on purpose: a running kernel may still read it
         d.ptr = p;
         d.len = len;

@@ -35,7 +35,7 @@ void count_launch(int n = 1);
 // entries 0..len-1, built lazily and grown on demand.  Returns a device pointer valid for the
 // life of the process.
 int fst_table(int gpu, int min_len, const double** table_dev);
-const double* fst_table_host(int min_len);
+double fst_value(int step);
 
 // nb_traj.cu: n_traj single-block persistent trajectories of the same n in one launch
 int launch_traj_batch(int math, int n, int n_traj, const TrajDesc* descs_dev, const double* fst_dev,

@@ -339,7 +339,7 @@ int nb_large_pack(int math, int n, const double* q_planar_dev, const double* m0_
                   int step_next, double* pos4_dev, void* stream) {
     (void)math;
     if (n < 1 || !q_planar_dev || !m0_dev || !is_device_dev || !pos4_dev || step_next < 0) return NB_ERR_ARG;
-    const double fst = fst_table_host(step_next + 1)[step_next];
+    const double fst = fst_value(step_next);
     large_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, q_planar_dev, m0_dev, is_device_dev, fst,
                                                                          (double4*)pos4_dev);
     count_launch();
@@ -385,7 +385,7 @@ static int large_step_impl(int math, int step, int n, int i_begin, int i_count, 
         NB_CUDA(cudaEventRecord(pe1, st));
         g_prof.evs.emplace_back(pe0, pe1);
     }
-    const double fst_next = fst_table_host(step + 2)[step + 1];
+    const double fst_next = fst_value(step + 1);
     if (peers)
         large_integrate_push_kernel<<<(i_count + 127) / 128, 128, 0, st>>>((const double4*)pos4_dev, *peers, vel_dev, m0_dev,
                                                                        is_device_dev, (const double*)scratch_dev, nsplit,

@@ -1,46 +1,59 @@
-// Whole-GPU cooperative persistent trajectory kernel: ONE system (or up to 4 systems of the same n
-// in lock step) spread over up to 128 SMs, all steps and observers in one launch.  This is the
-// low-step-latency path for the b512 / b1024 queries: a single block needs ~133 us per b1024 step
-// (nb_traj.cu), the FP64 floor over 128 SMs is ~1.05 us.
+// Whole-GPU persistent trajectory kernel: ONE system (or two systems of the same n in lock step) spread over
+// up to 128 SMs, all steps and observers in one launch.  This is the low-step-latency path for the b128 ... b1024
+// queries: a single block needs ~133 us per b1024 step (nb_traj.cu), the FP64 floor over 128 SMs is ~1.05 us.
 //
-// Replaces the host-driven per-step launch sequence of the reference (hw5.cu:368-404, 387-403,
-// 489-508: 3-4 kernel launches per step, 600 000-800 000 per trajectory).  Arithmetic: nbody.cc:51-89.
+// Replaces the host-driven per-step launch sequence of the reference (hw5.cu:368-404, 387-403, 489-508: 3-4
+// kernel launches per step, 600 000-800 000 per trajectory).  Arithmetic: nbody.cc:51-89.
 //
-// Block c owns bodies [8c, 8c+8) and is warp-specialised (384 threads):
-//   * 8 COMPUTE warps (2 per scheduler): warp w works on the body pair 8c + 2(w&3), +1 against half
-//     (w>>2) of every chunk of j records, its lanes taking consecutive slots; two i-bodies share every
-//     j record read from shared memory (shared-memory traffic = half the FP64 issue rate).  A
-//     transposing xor butterfly (15 instead of 30 64-bit shuffles) leaves the pair's sums in lanes 0
-//     and 16, the two j-halves meet in shared memory and threads 0..7 integrate one body each
-//     (v += a*dt, q += v*dt) and publish it.
-//   * 4 FETCH warps: warp f looks after producer blocks 32f..32f+31 (one per lane) = "chunk" f: waits
-//     for their sectors of the current step, copies them into shared memory and completes the chunk's
-//     mbarrier.  The compute warps consume chunk after chunk as they arrive, so the all-to-all
-//     exchange streams underneath the pair loop instead of in front of it, and with more than one
-//     trajectory per launch one system's exchange hides behind another's arithmetic.
+// Block c owns bodies [8c, 8c+8).  Every step each block needs the new positions of ALL bodies, so the step
+// latency is  hop (publish -> everybody has it)  +  pair loop  +  reduction/integration,  and the design goal
+// is a hop of about one L2 round trip:
 //
-// Exchange, measured design (tools/microbench/exchange_bench.cu, profiles/r01_exchange_microbench.md):
-// on B200 a release/acquire hop costs ~0.4-0.5 us per fence (MEMBAR.ALL.GPU) and an atomic-counter
-// grid barrier ~1.5 us, while an un-fenced store -> poll hop is ~0.37 us.  So there are no fences, no
-// atomics and no barrier object: every body is published as one naturally aligned 32-byte sector
-// {x, y, z, step tag} with a single 256-bit store, into a global record array double-buffered by step
-// parity (L2 resident).  A sector is the unit the L2 reads and writes, so a reader sees it entirely
-// old or entirely new and the tag validates the data it travels with; no ordering between different
-// sectors is assumed anywhere.  A fetch lane polls the tag of its producer's last sector (a block's 8
-// sectors leave in one store instruction), then loads the 8 sectors with 256-bit loads, re-reading
-// any whose tag is still old.  Reuse of a parity buffer is safe without fences: a block overwrites
-// step s-2's sectors only after it has consumed every block's step s-1 sectors, which each block
-// publishes only after its own reads of step s-2 have completed (data dependence).  Spins are bounded
-// (clock64) and raise `status`.
+//   * publish: a body leaves as one naturally aligned 32-byte sector {x, y, z, step tag} (one 256-bit store)
+//     into a global record array double-buffered by step parity (L2 resident).  No fence, no atomic, no flag:
+//     a sector is the unit the L2 reads and writes, so a reader sees it entirely old or entirely new and the
+//     tag validates the data it travels with.
+//   * fetch: one elected thread per block copies records with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+//     straight into shared memory, WITHOUT polling first: all blocks run in lock step, so a block's own
+//     publish time predicts everybody else's; the copy is issued a tuned delay after it.  Blocks form clusters
+//     of CS (default 4): block r of a cluster copies slice r of the record array and MULTICASTS it into the
+//     shared memory of all CS blocks, so the L2 serves 1/CS of the all-to-all traffic (4 MB -> 1 MB per b1024
+//     step; the L2 read bandwidth, not only its latency, bounds a 128-reader all-to-all).
+//   * validate: when the copies have landed, the 256 compute threads check every record's tag (4 each).  A record
+//     that was copied before its publication is stale: its thread polls that one sector in global memory and
+//     patches shared memory.  This is also what keeps the blocks in lock step - a block that runs ahead finds
+//     the slowest block's records stale and waits for them, nothing else synchronises the grid.  Correctness
+//     therefore never depends on the delay, only the speed does.
+//   * buffer reuse is safe without fences by data dependence: a block overwrites its step s-2 sectors (and a
+//     TMA overwrites the step s-2 stage in shared memory) only after its step s-1 data reached everybody, and
+//     every block publishes step s-1 only after it finished reading step s-2.
 //
-// Gravity devices are kept out of the streamed records' mass column (G*m = 0 there): their pair terms
-// are added at the end of the pair loop, when all positions of the previous step are in and the
-// observers (hit test, missile reach: hw5.cu:241-309) have decided whether the device still has mass.
+// Warp roles (320 threads):
+//   * 8 COMPUTE warps = 2 body groups x 4 j-quarters: warp w holds bodies 8c + 4(w>>2) .. +3 in registers and
+//     takes records 128k + 32(w&3) + lane: four i-bodies share every j record read from shared memory
+//     (conflict-free LDS.128 pairs: lanes with bit 2 set read the record's second half first).  A transposing
+//     xor butterfly (18 64-bit shuffles for 12 sums) leaves the sums in lanes 0/8/16/24; the four quarters
+//     meet in shared memory and 24 threads of warp 0 integrate one body component each (v += a*dt,
+//     q += v*dt), gather x, y, z by shuffle and publish.
+//   * 1 OBSERVER warp: hit test, minimum distance, missile reach/destroy (hw5.cu:241-309) on the complete
+//     positions of every step, off the critical path.  It also owns the gravity devices' masses: the mass
+//     column is double-buffered by step parity and the observer writes G*m_eff(step+2) of every device into
+//     the next stage, so the pair loop is oblivious to devices.  The one step on which a device is destroyed
+//     (its mass was written speculatively) is redone by the compute warps with the corrected column.
+//   * 1 PRODUCER thread: arms the stage's mbarrier with the expected byte count and issues the TMA copies.
 //
-// Shared memory per trajectory: pos[2][3*nslot] + gm[nslot]; body 8p+k of chunk f sits at slot
-// f*256 + k*32 + (p-32f): fetch lanes write consecutive 24-byte slots and compute lanes read them
-// (bank-conflict free for 8-byte accesses).  Co-residency of all blocks is guaranteed by the
-// cooperative launch (grid <= SM count, 1 block/SM).
+// Spins are bounded (clock64) and raise `status`; co-residency comes from the cooperative launch
+// (grid <= SM count, 1 block/SM).
+//
+// Measured on B200, b1024 (profiles/r01_grid_exchange_v2.md): 3.2-3.4 us/step for one system (copy delay 600-1200
+// clk, clusters of 2 or 4) against 4.4-4.9 us for the previous exchange (per-producer sentinel poll, then LDG
+// fetch warps: two dependent L2 round trips per step); in-kernel phases per step at 1.96 GHz: copy 1775 clk
+// (delay 900 + TMA round trip), validate 620, pairs 3200 (FP64 floor 2048), butterfly 515, integrate+publish 440.
+// Tried and measured worse: validating inside the pair loop (a vote per record batch serialises the loop),
+// optimistic pair loop + redo on a stale record (a redone block is late, all others find it stale: cascade),
+// per-block adaptive delays (creep up together), rotating the tag slot for conflict-free validation loads.
+#include <cooperative_groups.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -49,24 +62,22 @@
 #include "nb_math.cuh"
 
 namespace nb {
+
 namespace {
 
-constexpr int GB = 8;           // bodies per block
-constexpr int NCW = 8;          // compute warps: 4 body pairs x 2 j-halves
-constexpr int NFW = 4;          // fetch warps = chunks of 32 producer blocks
-constexpr int GT = 32 * (NCW + NFW);
-constexpr int CHUNK = 32 * GB;  // slots per chunk
-constexpr int MAX_T = 4;        // trajectories per launch (shared memory: 56 B x nslot each)
+constexpr int GB = 8;            // bodies per block
+constexpr int BPW = 4;           // bodies per compute warp
+constexpr int MAX_NJ = 8;        // compute warps = 2 body groups x NJ j-parts (NJ = 4 or 8); then the observer warp and
+                                 // the producer warp (lane 0 only)
+constexpr int MAX_T = 2;         // systems per launch (shared memory: 80 B per record each)
+constexpr int MAX_CS = 8;        // largest cluster
+constexpr int RPAD = 32 * MAX_NJ; // shared-memory stages hold a multiple of this many records
+constexpr int FLAG_STOP = 1, FLAG_REDO = 2;
 constexpr long long SPIN_LIMIT = 4000000000LL;  // ~2 s of SM clocks
+constexpr int NPROF = 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ double ld_strong_d(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// one naturally aligned 32-byte sector per access (SASS LDG/STG.E.ENL2.256): the unit the L2 reads and
-// writes, so a sector is observed either entirely old or entirely new
+// one naturally aligned 32-byte sector per access (SASS LDG/STG.E.ENL2.256)
 __device__ __forceinline__ void ld_sector(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
@@ -79,6 +90,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -90,409 +104,538 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory"); }
+// 1-D TMA bulk copy global -> shared memory of this block; completion (bytes) counted on the block's mbarrier
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// the same, delivered to the same shared-memory offset (and mbarrier) of every block in cta_mask
+__device__ __forceinline__ void tma_load_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+template <int NTHREADS>
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-struct TState {  // per trajectory, per COMPUTE thread (registers after unrolling)
-    int n_dev, kind, Ps, As, DDs, DD, step, step_begin, step_end;  // Ps/As/DDs: slots of planet/asteroid/device
+// Record layout: one 32-byte sector {x, y, z, step tag}: the unit the L2 reads and writes.
+__device__ __forceinline__ double make_tag(int step) { return __longlong_as_double((long long)step); }
+__device__ __forceinline__ bool tag_is(double tg, int step) { return __double_as_longlong(tg) == (long long)step; }
+
+struct Shared {
+    // stage = step parity.  full: the copies of all R records have landed (1 arrival = the producer's expect_tx, plus
+    // the bytes); obs: the observer has judged the step (1 arrival).  Each completes once per two steps.
+    alignas(8) uint64_t full[MAX_T][2];
+    alignas(8) uint64_t obs[MAX_T][2];
+    volatile int flags[MAX_T][2];   // FLAG_* of the step held by the stage, valid once obs completed
+    volatile int pubstep[MAX_T];    // the step whose partial sums are complete in this block (producer trigger)
+    volatile int stop[MAX_T];
+    volatile int abort;
+    double part[2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part
+};
+
+struct ObsState {  // per system, observer warp
+    int n_dev, kind, Prec, Arec, DDrec, DD, step, step_begin, step_end;
     bool q3_armed, active, observed;
     double min_d2, cost;
     int argmin_step, hit_step, destroyed_step;
-    // device bookkeeping (lane k < n_dev, every compute warp; reach steps are reported by block 0 warp 0)
-    int my_dev, my_slot, my_reach;
+    int my_dev, my_reach;  // lane k < n_dev
     double my_m0;
-    // integrator threads (tid < 8): the body's velocity and position
-    double v[3], q[3];
-    double fst_next;  // |sin| of the next step, prefetched one step ahead
 };
 
-// PROFILE: block 0 thread 0 accumulates clock64 per phase into prof[0..7] (NB_GRID_PROFILE=1, T == 1 only)
-template <int MATH, int T, bool PROFILE>
-__global__ void __launch_bounds__(GT, 1)
+// PROFILE: block 0 thread 0 accumulates clock64 per phase (NB_GRID_PROFILE=1)
+template <int MATH, int T, int NJ, bool PROFILE>
+__global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 long long* __restrict__ prof, int* __restrict__ status, int nchunk, unsigned poll_sleep_ns) {
-    extern __shared__ double smem[];
-    __shared__ volatile int s_abort;
-    __shared__ volatile int s_stop[T];
-    __shared__ double s_part[2][NCW][6];  // per warp: partial sums {ax,ay,az} of body A then body B over its j-half
-    // chunk f of trajectory t, stage = step parity: full = the fetch warp has filled it (1 arrival), empty = the 8
-    // compute warps are done with it.  A stage's barriers complete once per two steps, and the fetch warp waits
-    // for "empty" before refilling, so a phase can never be lapped by a waiter (no parity aliasing).
-    __shared__ alignas(8) uint64_t s_full[T][NFW][2];
-    __shared__ alignas(8) uint64_t s_empty[T][NFW][2];
+                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = blockIdx.x, C = gridDim.x;
+    const int c = blockIdx.x;
     const int n = descs[0].n;
-    const int nslot = nchunk * CHUNK;
-    auto slot_of = [&](int b) {
-        const int p = b / GB, k = b % GB;
-        return (p >> 5) * CHUNK + k * 32 + (p & 31);
-    };
-    // per trajectory: pos[2][3*nslot] (slot-major x,y,z) then gm[nslot]
-    auto s_pos = [&](int t, int buf) { return smem + (size_t)t * 7 * nslot + (size_t)buf * 3 * nslot; };
-    auto s_gm = [&](int t) { return smem + (size_t)t * 7 * nslot + 6 * nslot; };
+    constexpr int NCW = 2 * NJ, W_OBS = NCW, W_PROD = NCW + 1, GT = 32 * (NCW + 2), RQ = 32 * NJ;
+    const int RS = (R + RPAD - 1) / RPAD * RPAD;  // records per stage in shared memory (tail beyond R: zero mass, never copied)
+    // per system: pos[2][RS] records {x, y, z, tag} then gm[2][RS]
+    auto s_pos = [&](int t, int stage) { return smem + (size_t)t * 10 * RS + (size_t)stage * 4 * RS; };
+    auto s_gm = [&](int t, int stage) { return smem + (size_t)t * 10 * RS + 8 * RS + (size_t)stage * RS; };
+    auto g_rec = [&](int t, int st) { return gbuf + ((size_t)(st & 1) * T + t) * (size_t)R * 4; };
 
     if (tid == 0) {
-        s_abort = 0;
+        sh.abort = 0;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            // a trajectory that stopped in an earlier launch never steps again: keep its fetch warps out
-            s_stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
-            for (int f = 0; f < NFW; f++)
-                for (int b = 0; b < 2; b++) {
-                    mbar_init(&s_full[t][f][b], 1);
-                    mbar_init(&s_empty[t][f][b], NCW);
-                }
+            // a trajectory that stopped in an earlier launch never steps again
+            sh.stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
+            sh.pubstep[t] = descs[t].step_begin;
+            for (int b = 0; b < 2; b++) {
+                mbar_init(&sh.full[t][b], 1);
+                mbar_init(&sh.obs[t][b], 1);
+                sh.flags[t][b] = 0;
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // positions of step_begin into buffer (step_begin & 1); static G*m (0 for devices and padding)
+    // positions of step_begin (tagged) into stage (step_begin & 1); static G*m in both mass columns, the devices'
+    // G*m_eff(step_begin + 1) in the current one (the observer fills the other)
 #pragma unroll
     for (int t = 0; t < T; t++) {
         const TrajDesc& d = descs[t];
-        double* p0 = s_pos(t, d.step_begin & 1);
-        double* p1 = s_pos(t, (d.step_begin & 1) ^ 1);
-        for (int sl = tid; sl < nslot; sl += GT) {
-            const int f = sl / CHUNK, k = (sl % CHUNK) / 32, lp = sl % 32;
-            const int p = 32 * f + lp;
-            const int b = p < C ? p * GB + k : n;
-            double x = 0, y = 0, z = 0, g = 0;
-            if (b < n) {
-                x = d.q[b], y = d.q[b + n], z = d.q[b + 2 * n];
-                g = d.is_device[b] ? 0.0 : gm_eff(d.m[b], false, 0.0);
+        const int sb = d.step_begin;
+        double* p0 = s_pos(t, sb & 1);
+        double* p1 = s_pos(t, (sb & 1) ^ 1);
+        double* g0 = s_gm(t, sb & 1);
+        double* g1 = s_gm(t, (sb & 1) ^ 1);
+        const double f1 = fst[sb + 1];
+        for (int r = tid; r < RS; r += GT) {
+            double x = 0, y = 0, z = 0, ga = 0, gb = 0;
+            if (r < n) {
+                x = d.q[r], y = d.q[r + n], z = d.q[r + 2 * n];
+                const bool dev = d.is_device[r];
+                ga = gm_eff(d.m[r], dev, f1);
+                gb = dev ? 0.0 : ga;
             }
-            p0[3 * sl] = x, p0[3 * sl + 1] = y, p0[3 * sl + 2] = z;
-            p1[3 * sl] = 0.0, p1[3 * sl + 1] = 0.0, p1[3 * sl + 2] = 0.0;
-            s_gm(t)[sl] = g;
+            p0[4 * r] = x, p0[4 * r + 1] = y, p0[4 * r + 2] = z, p0[4 * r + 3] = make_tag(sb);
+            p1[4 * r] = 0.0, p1[4 * r + 1] = 0.0, p1[4 * r + 2] = 0.0, p1[4 * r + 3] = make_tag(-1);
+            g0[r] = ga, g1[r] = gb;
         }
     }
     __syncthreads();
+    cluster_sync_all();  // every block's mbarriers exist before anybody multicasts into them
 
-    if (warp >= NCW) {
-        // ------------------------------------------------------------------ FETCH warps
-        const int f = warp - NCW;
-        const int p = 32 * f + lane;  // producer block this lane looks after
-        const bool have = p < C;
-        int fstep[T], fend[T];
-        bool factive[T];
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            fstep[t] = descs[t].step_begin;
-            fend[t] = descs[t].step_end;
-            factive[t] = f < nchunk;
+    // the sector of record r once it carries the tag of step `st`, polled in global memory
+    auto poll_rec = [&](const double* grec, int r, int st, double& x, double& y, double& z, double& tg) {
+        const long long t0 = clock64();
+        do {
+            ld_sector(grec + 4 * (size_t)r, x, y, z, tg);
+            if (clock64() - t0 > SPIN_LIMIT) {
+                sh.abort = 1;
+                atomicExch(status, 1);
+                break;
+            }
+        } while (!tag_is(tg, st));
+    };
+    // A record of step `st` for the observer: out of shared memory if its tag is current, else out of global memory.
+    // The compute warps patch stale shared-memory records coordinates first, tag last (patch_rec), so the tag is read first.
+    auto load_rec = [&](const double* pos, const double* grec, int r, int st, double& x, double& y, double& z) {
+        const volatile double* vp = pos + 4 * r;
+        double tg = vp[3];
+        if (tag_is(tg, st)) {
+            __threadfence_block();
+            x = vp[0], y = vp[1], z = vp[2];
+        } else {
+            poll_rec(grec, r, st, x, y, z, tg);
         }
-        bool any = f < nchunk;
-        while (any) {
-            any = false;
+    };
+    // fetch a stale record from global memory and patch shared memory: coordinates, fence, then the tag
+    auto patch_rec = [&](double* pos, const double* grec, int r, int st) {
+        double x, y, z, tg;
+        poll_rec(grec, r, st, x, y, z, tg);
+        pos[4 * r] = x, pos[4 * r + 1] = y, pos[4 * r + 2] = z;
+        __threadfence_block();
+        pos[4 * r + 3] = tg;
+    };
+    // bounded wait on an mbarrier phase; false = aborted
+    auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+        if (mbar_try_wait(bar, parity)) return true;
+        const long long t0 = clock64();
+        while (!mbar_try_wait(bar, parity)) {
+            if (sh.abort) return false;
+            if (clock64() - t0 > SPIN_LIMIT) {
+                sh.abort = 1;
+                atomicExch(status, 1);
+                return false;
+            }
+        }
+        return true;
+    };
+
+    if (warp == W_PROD) {
+        // ------------------------------------------------------------------ PRODUCER thread
+        if (lane == 0) {
+            const uint32_t CS = cluster_nctarank(), rank = cluster_ctarank();
+            const uint32_t slice = (uint32_t)R / CS;  // records per cluster rank (R is a multiple of 8*CS)
+            const uint16_t mask = (uint16_t)((1u << CS) - 1u);
+            int pstep[T];
+            bool pact[T];
+            bool any = false;
 #pragma unroll
             for (int t = 0; t < T; t++) {
-                if (!factive[t]) continue;
-                if (fstep[t] >= fend[t]) {
-                    factive[t] = false;
-                    continue;
-                }
-                const int st = ++fstep[t];
-                const long long tag = (long long)st;
-                const double* sec = gbuf + ((size_t)(st & 1) * T + t) * C * GB * 4;
-                const double* mine = sec + (size_t)(have ? p : 0) * GB * 4;
-                // wait until every producer of the chunk has published step st (or the trajectory stopped)
-                bool stopped = false;
-                {
+                pstep[t] = descs[t].step_begin;
+                pact[t] = !sh.stop[t] && descs[t].step_end > descs[t].step_begin;
+                any |= pact[t];
+            }
+            while (any && !sh.abort) {
+                any = false;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    if (!pact[t]) continue;
+                    const int st = pstep[t] + 1;
+                    // this block's sums of step st are complete: it publishes within ~150 clk, and so does everybody
                     const long long t0 = clock64();
-                    bool ready = !have;
-                    for (;;) {
-                        if (!ready) ready = __double_as_longlong(ld_strong_d(mine + (GB - 1) * 4 + 3)) == tag;
-                        if (__all_sync(0xffffffffu, ready)) break;
-                        if (poll_sleep_ns) __nanosleep(poll_sleep_ns);  // leave the issue slots and the L2 to the others
-                        if (s_stop[t] || s_abort) {
-                            stopped = true;
+                    bool go = true;
+                    while (sh.pubstep[t] < st) {
+                        if (sh.stop[t] || sh.abort) {
+                            go = false;
                             break;
                         }
                         if (clock64() - t0 > SPIN_LIMIT) {
-                            s_abort = 1;
+                            sh.abort = 1;
                             atomicExch(status, 1);
-                            stopped = true;
+                            go = false;
                             break;
                         }
                     }
-                }
-                stopped = __any_sync(0xffffffffu, stopped);
-                if (stopped) {
-                    factive[t] = false;
-                    continue;
-                }
-                {   // the stage's previous contents (step st-2) must have been consumed by the compute warps
-                    const int uses = (st - descs[t].step_begin) >> 1;
-                    if (uses >= 1) {
-                        const long long t0 = clock64();
-                        while (!mbar_try_wait(&s_empty[t][f][st & 1], (uint32_t)(uses - 1) & 1u)) {
-                            if (s_abort || clock64() - t0 > SPIN_LIMIT) {
-                                s_abort = 1;
-                                break;
-                            }
-                        }
+                    if (!go) {
+                        pact[t] = false;
+                        continue;
                     }
-                }
-                if (have) {
-                    double x[GB], y[GB], z[GB], g[GB];
-#pragma unroll
-                    for (int k = 0; k < GB; k++) ld_sector(mine + 4 * k, x[k], y[k], z[k], g[k]);
-                    double* dst = s_pos(t, st & 1) + 3 * (f * CHUNK + lane);
-                    const long long t0 = clock64();
-#pragma unroll
-                    for (int k = 0; k < GB; k++) {
-                        while (__double_as_longlong(g[k]) != tag) {  // overtaken by the sentinel's store: read again
-                            ld_sector(mine + 4 * k, x[k], y[k], z[k], g[k]);
-                            if (clock64() - t0 > SPIN_LIMIT) {
-                                s_abort = 1;
-                                atomicExch(status, 1);
-                                break;
-                            }
-                        }
-                        double* o = dst + 3 * 32 * k;
-                        o[0] = x[k], o[1] = y[k], o[2] = z[k];
+                    const long long t1 = clock64();
+                    uint64_t* bar = &sh.full[t][st & 1];
+                    mbar_arrive_expect_tx(bar, (uint32_t)R * 32u);
+                    // Copy delay after the trigger: long enough for everybody's sectors of this step to be in the L2 when the
+                    // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
+                    // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
+                    while (clock64() - t1 < delay_clk) {
                     }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s_full[t][f][st & 1]);
-                any = true;
-            }
-            if (s_abort) break;
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------------- COMPUTE warps
-    const int pairA = c * GB + 2 * (warp & 3);  // the warp's two bodies: pairA, pairA + 1
-    const int half = warp >> 2;
-    const int my_body = c * GB + tid;            // integrator threads tid < 8
-    const bool integ = tid < GB && my_body < n;
-    const int slotA = slot_of(min(pairA, GB * C - 1)), slotB = slot_of(min(pairA + 1, GB * C - 1));
-
-    TState ts[T];
-    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
-    auto tick = [&](int phase) {
-        if (PROFILE) {
-            const long long now = clock64();
-            pacc[phase] += now - pt;
-            pt = now;
-        }
-    };
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-        const TrajDesc& d = descs[t];
-        TState& s = ts[t];
-        s.n_dev = d.n_dev, s.kind = d.kind, s.DD = d.destroy_device;
-        s.Ps = slot_of(d.planet), s.As = slot_of(d.asteroid);
-        s.DDs = (s.DD >= 0 && s.DD < n) ? slot_of(s.DD) : 0;
-        s.step = s.step_begin = d.step_begin, s.step_end = d.step_end;
-        s.min_d2 = d.ev->min_d2, s.argmin_step = d.ev->argmin_step, s.hit_step = d.ev->hit_step;
-        s.destroyed_step = d.ev->destroyed_step, s.cost = d.ev->cost;
-        s.q3_armed = (s.kind == NB_KIND_Q3) && s.DD >= 0 && s.DD < n && d.m[s.DD] != 0.0;
-        s.active = !((s.kind >= NB_KIND_Q2) && s.hit_step != -2);
-        s.observed = d.ev->steps_done >= s.step;
-        s.my_dev = -1, s.my_slot = 0, s.my_reach = -2, s.my_m0 = 0.0;
-        if (lane < s.n_dev) {
-            s.my_dev = d.dev_index[lane];
-            s.my_slot = slot_of(s.my_dev);
-            s.my_m0 = d.m[s.my_dev];
-            s.my_reach = d.ev->reach_step[lane];
-        }
-        s.fst_next = fst[s.step + 1];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            s.v[k] = integ ? d.v[k * n + my_body] : 0.0;
-            s.q[k] = integ ? d.q[k * n + my_body] : 0.0;
-        }
-    }
-
-    // observers of step s.step on its (complete) position buffer; uniform over all compute threads except the
-    // per-device reach test
-    auto observe = [&](TState& s, int t) {
-        const double* pos = s_pos(t, s.step & 1);
-        const double* p = pos + 3 * s.Ps;
-        const double* a = pos + 3 * s.As;
-        const double px = p[0], py = p[1], pz = p[2];
-        const double d2 = dist2_rn(px, py, pz, a[0], a[1], a[2]);
-        if (d2 < s.min_d2) {  // hw5.cu:245-247
-            s.min_d2 = d2;
-            s.argmin_step = s.step;
-        }
-        if (s.kind == NB_KIND_Q2 && s.my_dev >= 0 && s.my_reach == -2) {  // hw5.cu:265-287
-            const double* dv = pos + 3 * s.my_slot;
-            const double md = __dmul_rn(MISSILE_STEP, (double)s.step);
-            if (dist2_rn(px, py, pz, dv[0], dv[1], dv[2]) < __dmul_rn(md, md)) s.my_reach = s.step;
-        }
-        if (s.kind >= NB_KIND_Q2) {
-            if (d2 < PLANET_RADIUS2) {  // nbody.cc:134, hw5.cu:295-298
-                s.hit_step = s.step;
-                s.active = false;
-            } else if (s.q3_armed && s.destroyed_step == -2) {  // hw5.cu:299-307
-                const double* dv = pos + 3 * s.DDs;
-                const double md = __dmul_rn(MISSILE_STEP, (double)s.step);
-                if (dist2_rn(px, py, pz, dv[0], dv[1], dv[2]) < __dmul_rn(md, md)) {
-                    s.destroyed_step = s.step;
-                    s.cost = __dadd_rn(1e5, __dmul_rn(1e3, __dmul_rn((double)(s.step + 1), DT)));
+                    double* dst = s_pos(t, st & 1) + (size_t)rank * slice * 4;
+                    const double* src = g_rec(t, st) + (size_t)rank * slice * 4;
+                    if (CS == 1)
+                        tma_load(dst, src, slice * 32u, bar);
+                    else
+                        tma_load_multicast(dst, src, slice * 32u, bar, mask);
+                    pstep[t] = st;
+                    if (st >= descs[t].step_end) pact[t] = false;
+                    any |= pact[t];
                 }
             }
         }
-        s.observed = true;
-    };
-
-    bool any = false;
-#pragma unroll
-    for (int t = 0; t < T; t++) any |= ts[t].active;
-    long long g0 = 0, c0 = 0;
-    if (PROFILE) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-        c0 = clock64();
-    }
-    int pbuf = 0;  // s_part double buffer
-
-    while (any) {
+    } else if (warp == W_OBS) {
+        // ------------------------------------------------------------------ OBSERVER warp
+        ObsState os[T];
+        bool any = false;
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            TState& s = ts[t];
-            if (!s.active) continue;  // uniform across the grid
-            if (PROFILE) pt = clock64();
-            // state: integrator threads hold q, v of step s.step; buffer (s.step & 1) receives the positions of
-            // step s.step chunk by chunk (it is complete already when s.step == step_begin)
-            const bool last = s.step >= s.step_end;
-            const bool wait_chunks = s.step > s.step_begin;
-            const uint32_t parity = (uint32_t)((s.step - s.step_begin - 1) >> 1) & 1u;  // fill index of this stage
-            const int stage = s.step & 1;
-            const double* cpos = s_pos(t, s.step & 1);
-            const double* cg = s_gm(t);
-            double ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
-            double xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
-            bool aborted = false;
-            // (1) forces on the warp's two bodies (nbody.cc:56-74), chunk by chunk as the positions arrive.
-            //     The warp's own bodies live in the block's own chunk, so that chunk is awaited first.
-            const int fown = c >> 5;
-            for (int ff = 0; ff < nchunk; ff++) {
-                const int f = ff == 0 ? fown : (ff <= fown ? ff - 1 : ff);
-                if (wait_chunks) {
-                    const long long t0 = clock64();
-                    while (!mbar_try_wait(&s_full[t][f][stage], parity)) {
-                        if (s_abort || clock64() - t0 > SPIN_LIMIT) {
-                            aborted = true;
-                            break;
+            const TrajDesc& d = descs[t];
+            ObsState& s = os[t];
+            s.n_dev = d.n_dev, s.kind = d.kind, s.DD = d.destroy_device;
+            s.Prec = d.planet, s.Arec = d.asteroid;
+            s.DDrec = (s.DD >= 0 && s.DD < n) ? s.DD : 0;
+            s.step = s.step_begin = d.step_begin, s.step_end = d.step_end;
+            s.min_d2 = d.ev->min_d2, s.argmin_step = d.ev->argmin_step, s.hit_step = d.ev->hit_step;
+            s.destroyed_step = d.ev->destroyed_step, s.cost = d.ev->cost;
+            s.q3_armed = (s.kind == NB_KIND_Q3) && s.DD >= 0 && s.DD < n && d.m[s.DD] != 0.0;
+            s.active = !((s.kind >= NB_KIND_Q2) && s.hit_step != -2);
+            s.observed = d.ev->steps_done >= s.step;
+            s.my_dev = -1, s.my_reach = -2, s.my_m0 = 0.0;
+            if (lane < s.n_dev) {
+                s.my_dev = d.dev_index[lane];
+                s.my_m0 = d.m[s.my_dev];
+                s.my_reach = d.ev->reach_step[lane];
+            }
+            any |= s.active;
+        }
+        while (any && !sh.abort) {
+            any = false;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                ObsState& s = os[t];
+                if (!s.active) continue;
+                const int st = s.step, stage = st & 1;
+                if (st > s.step_begin && !wait_bar(&sh.full[t][stage], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u)) {
+                    s.active = false;
+                    continue;
+                }
+                const double* pos = s_pos(t, stage);
+                const double* grec = g_rec(t, st);
+                int flags = 0;
+                if (!s.observed) {
+                    double px, py, pz, ax, ay, az;
+                    load_rec(pos, grec, s.Prec, st, px, py, pz);
+                    load_rec(pos, grec, s.Arec, st, ax, ay, az);
+                    const double d2 = dist2_rn(px, py, pz, ax, ay, az);
+                    if (d2 < s.min_d2) {  // hw5.cu:245-247
+                        s.min_d2 = d2;
+                        s.argmin_step = st;
+                    }
+                    if (s.kind == NB_KIND_Q2 && s.my_dev >= 0 && s.my_reach == -2) {  // hw5.cu:265-287
+                        double dx, dy, dz;
+                        load_rec(pos, grec, s.my_dev, st, dx, dy, dz);
+                        const double md = __dmul_rn(MISSILE_STEP, (double)st);
+                        if (dist2_rn(px, py, pz, dx, dy, dz) < __dmul_rn(md, md)) s.my_reach = st;
+                    }
+                    if (s.kind >= NB_KIND_Q2) {
+                        if (d2 < PLANET_RADIUS2) {  // nbody.cc:134, hw5.cu:295-298
+                            s.hit_step = st;
+                            flags |= FLAG_STOP;
+                        } else if (s.q3_armed && s.destroyed_step == -2) {  // hw5.cu:299-307
+                            double dx, dy, dz;
+                            load_rec(pos, grec, s.DDrec, st, dx, dy, dz);
+                            const double md = __dmul_rn(MISSILE_STEP, (double)st);
+                            if (dist2_rn(px, py, pz, dx, dy, dz) < __dmul_rn(md, md)) {
+                                s.destroyed_step = st;
+                                s.cost = __dadd_rn(1e5, __dmul_rn(1e3, __dmul_rn((double)(st + 1), DT)));
+                                // the pair loop of this step ran (or runs) with the device's mass: redo it without
+                                if (st < s.step_end) flags |= FLAG_REDO;
+                                if (lane == 0) s_gm(t, stage)[s.DDrec] = 0.0;
+                            }
                         }
                     }
-                    if (aborted) break;
                 }
-                if (ff == 0) {
-                    xa = cpos[3 * slotA], ya = cpos[3 * slotA + 1], za = cpos[3 * slotA + 2];
-                    xb = cpos[3 * slotB], yb = cpos[3 * slotB + 1], zb = cpos[3 * slotB + 2];
+                if (st >= s.step_end) flags |= FLAG_STOP;
+                if (!(flags & FLAG_STOP) && s.my_dev >= 0) {
+                    // mass column of the next step's positions: G*m_eff(st + 2) (nbody.cc:14-16, 61-64), 0 once destroyed
+                    const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev == s.DD && s.destroyed_step != -2;
+                    s_gm(t, stage ^ 1)[s.my_dev] = gm_eff(gone ? 0.0 : s.my_m0, true, fst[st + 2]);
                 }
-                if (!last) {
-                    const int j0 = f * CHUNK + half * (CHUNK / 2) + lane;
+                __syncwarp();
+                if (lane == 0) {
+                    sh.flags[t][stage] = flags;
+                    mbar_arrive(&sh.obs[t][stage]);  // release: the mass column writes above are visible to the waiters
+                }
+                s.observed = false;
+                if (flags & FLAG_STOP)
+                    s.active = false;
+                else
+                    s.step = st + 1;
+                any |= s.active;
+            }
+        }
+        // events (block 0 reports; every block computed the same)
+        if (c == 0) {
 #pragma unroll
-                    for (int k = 0; k < CHUNK / 64; k++) {
-                        const int j = j0 + 32 * k;
-                        const double jx = cpos[3 * j], jy = cpos[3 * j + 1], jz = cpos[3 * j + 2], jg = cg[j];
-                        pair<MATH>(xa, ya, za, jx, jy, jz, jg, ax0, ay0, az0);
-                        pair<MATH>(xb, yb, zb, jx, jy, jz, jg, ax1, ay1, az1);
+            for (int t = 0; t < T; t++) {
+                const TrajDesc& d = descs[t];
+                ObsState& s = os[t];
+                if (lane < s.n_dev) d.ev->reach_step[lane] = s.my_reach;
+                if (lane == 0) {
+                    d.ev->min_d2 = s.min_d2;
+                    d.ev->argmin_step = s.argmin_step;
+                    d.ev->hit_step = s.hit_step;
+                    d.ev->destroyed_step = s.destroyed_step;
+                    d.ev->cost = s.cost;
+                    d.ev->steps_done = s.step;
+                    d.ev->n_reach = s.n_dev;
+                    if (s.kind == NB_KIND_Q3 && s.destroyed_step != -2) d.m[s.DD] = 0.0;  // hw5.cu:306
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ COMPUTE warps
+        const int bg = warp / NJ, part = warp % NJ;
+        const int body0 = c * GB + bg * BPW;  // the warp's four bodies (records body0 .. body0+3)
+        const int hsel = (lane >> 2) & 1;     // conflict-free LDS.128 pairs: these lanes read the second half first
+        // integrator threads (warp 0, lane < 24): body 8c + lane/3, component lane%3
+        const int ib = lane / 3, ik = lane - 3 * ib;
+        const int my_body = c * GB + ib;
+        const bool integ = warp == 0 && lane < 3 * GB;
+        int cstep[T], cbegin[T], cend[T];
+        bool cact[T];
+        double iq[T], iv[T];
+        long long pacc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
+        unsigned long long n_stale = 0;
+        auto tick = [&](int phase) {
+            if (PROFILE) {
+                const long long now = clock64();
+                pacc[phase] += now - pt;
+                pt = now;
+            }
+        };
+        bool any = false;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const TrajDesc& d = descs[t];
+            cstep[t] = cbegin[t] = d.step_begin, cend[t] = d.step_end;
+            cact[t] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
+            const bool mine = integ && my_body < n;
+            iq[t] = mine ? d.q[ik * n + my_body] : 0.0;
+            iv[t] = mine ? d.v[ik * n + my_body] : 0.0;
+            any |= cact[t];
+        }
+        long long g0 = 0, c0 = 0;
+        if (PROFILE) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+            c0 = clock64();
+        }
+        int pbuf = 0;
+        bool aborted = false;
+
+        while (any && !aborted) {
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                if (!cact[t]) continue;  // uniform across the grid
+                if (PROFILE) pt = clock64();
+                const int st = cstep[t], stage = st & 1;
+                const bool last = st >= cend[t];
+                // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
+                if (!last && st > cbegin[t]) wait_bar(&sh.full[t][stage], (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u);
+                tick(0);
+                double* pos = s_pos(t, stage);
+                const double* cg = s_gm(t, stage);
+                const double* grec = g_rec(t, st);
+                double ax[BPW], ay[BPW], az[BPW];
+                int flags = 0;
+                if (!last) {
+                    // (0) validate: every record of the stage must carry this step's tag (thread tid checks records
+                    //     tid + 256k; the rotating tag slot makes each warp's LDS.64 conflict-free).  A stale record was copied
+                    //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
+                    //     memory and patch shared memory, each stale record by exactly one thread of the block.
+                    bool patched = false;
+                    double tgv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int r = tid + 256 * k;
+                        tgv[k] = r < R ? pos[4 * r + 3] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int r = tid + 256 * k;
+                        if (r < R && !tag_is(tgv[k], st)) {
+                            patch_rec(pos, grec, r, st);
+                            patched = true;
+                            n_stale++;
+                        }
+                    }
+                    // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
+                    if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    compute_bar<32 * NCW>();
+                }
+                tick(5);
+                for (int attempt = 0; attempt < 2; attempt++) {
+#pragma unroll
+                    for (int i = 0; i < BPW; i++) ax[i] = ay[i] = az[i] = 0.0;
+                    if (!last) {
+                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records
+                        double xi[BPW], yi[BPW], zi[BPW];
+#pragma unroll
+                        for (int i = 0; i < BPW; i++) {
+                            const double* p = pos + 4 * (body0 + i);
+                            xi[i] = p[0], yi[i] = p[1], zi[i] = p[2];
+                        }
+#pragma unroll 2
+                        for (int r = 32 * part + lane; r < RS; r += RQ) {
+                            // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
+                            const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
+                            const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
+                            const double jx = hsel ? B.x : A.x, jy = hsel ? B.y : A.y, jz = hsel ? A.x : B.x;
+                            const double jg = cg[r];
+#pragma unroll
+                            for (int i = 0; i < BPW; i++) pair<MATH>(xi[i], yi[i], zi[i], jx, jy, jz, jg, ax[i], ay[i], az[i]);
+                        }
+                    }
+                    tick(1);
+                    // (2) the observer's verdict on the positions of step st
+                    flags = wait_bar(&sh.obs[t][stage], (uint32_t)((st - cbegin[t]) >> 1) & 1u) ? sh.flags[t][stage] : 0;
+                    if (!(flags & FLAG_REDO)) break;  // else: the device was destroyed at this very step, once per trajectory
+                }
+                tick(2);
+                if (flags & FLAG_STOP) {
+                    cact[t] = false;
+                    if (tid == 0) sh.stop[t] = 1;  // releases the producer
+                    continue;
+                }
+                // (3) transposing butterfly: 12 sums -> lanes 0/8/16/24 hold body 0/1/2/3
+                {
+                    const bool h16 = lane & 16, h8 = lane & 8;
+                    double k[6];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        // lanes with bit 4 clear keep bodies 0,1 and give away 2,3
+                        const double sx = h16 ? ax[i] : ax[i + 2], sy = h16 ? ay[i] : ay[i + 2], sz = h16 ? az[i] : az[i + 2];
+                        k[3 * i + 0] = (h16 ? ax[i + 2] : ax[i]) + __shfl_xor_sync(0xffffffffu, sx, 16);
+                        k[3 * i + 1] = (h16 ? ay[i + 2] : ay[i]) + __shfl_xor_sync(0xffffffffu, sy, 16);
+                        k[3 * i + 2] = (h16 ? az[i + 2] : az[i]) + __shfl_xor_sync(0xffffffffu, sz, 16);
+                    }
+                    double m0, m1, m2;
+                    {
+                        const double s0 = h8 ? k[0] : k[3], s1 = h8 ? k[1] : k[4], s2 = h8 ? k[2] : k[5];
+                        m0 = (h8 ? k[3] : k[0]) + __shfl_xor_sync(0xffffffffu, s0, 8);
+                        m1 = (h8 ? k[4] : k[1]) + __shfl_xor_sync(0xffffffffu, s1, 8);
+                        m2 = (h8 ? k[5] : k[2]) + __shfl_xor_sync(0xffffffffu, s2, 8);
+                    }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) {
+                        m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+                        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+                        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+                    }
+                    if ((lane & 7) == 0) {
+                        double* dstp = &sh.part[pbuf][warp][3 * (lane >> 3)];
+                        dstp[0] = m0, dstp[1] = m1, dstp[2] = m2;
                     }
                 }
-            }
-            // an abort (exchange timeout) is seen by every compute warp in this same iteration, before compute_bar
-            if (aborted) return;
-            tick(0);
-            // (2) all positions of step s.step are in: observers (hw5.cu:241-309)
-            if (!s.observed) observe(s, t);
-            if (last) s.active = false;
-            if (!s.active) {
-                if (tid == 0) s_stop[t] = 1;  // releases the fetch warps of this trajectory
-                continue;
-            }
-            const int st = ++s.step;
-            s.observed = false;
-            // (3) the gravity devices' pair terms with G*m_eff(st) (nbody.cc:14-16, 61-64); a destroyed device has mass 0
-            if (half == 0 && s.my_dev >= 0) {
-                const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev == s.DD && s.destroyed_step != -2;
-                const double g = gm_eff(gone ? 0.0 : s.my_m0, true, s.fst_next);
-                const double* dv = cpos + 3 * s.my_slot;
-                pair<MATH>(xa, ya, za, dv[0], dv[1], dv[2], g, ax0, ay0, az0);
-                pair<MATH>(xb, yb, zb, dv[0], dv[1], dv[2], g, ax1, ay1, az1);
-            }
-            s.fst_next = fst[st + 1];
-            // this warp is done with the positions of step st-1: hand the stage back to the fetch warps
-            __syncwarp();
-            if (lane == 0)
-                for (int f = 0; f < nchunk; f++) mbar_arrive(&s_empty[t][f][stage]);
-            // transposing butterfly: lanes with bit 4 clear keep body A's sums, the others body B's
-            {
-                const bool hi = lane & 16;
-                const double s0 = hi ? ax0 : ax1, s1 = hi ? ay0 : ay1, s2 = hi ? az0 : az1;  // what the partner keeps
-                double k0 = hi ? ax1 : ax0, k1 = hi ? ay1 : ay0, k2 = hi ? az1 : az0;        // what this lane keeps
-                k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-                k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                k2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                tick(3);
+                compute_bar<32 * NCW>();
+                if (sh.abort) {  // an exchange wait timed out somewhere in this block
+                    aborted = true;
+                    break;
+                }
+                // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
+                //     tagged sector {x, y, z, step}, unfenced
+                if (warp == 0) {
+                    if (lane == 0) sh.pubstep[t] = st + 1;  // producer trigger: everybody publishes within ~150 clk
+                    if (integ) {
+                        const double* p = &sh.part[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
+                        double a = p[0];
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {
-                    k0 += __shfl_xor_sync(0xffffffffu, k0, o);
-                    k1 += __shfl_xor_sync(0xffffffffu, k1, o);
-                    k2 += __shfl_xor_sync(0xffffffffu, k2, o);
+                        for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
+                        if (my_body < n) kick_drift(a, iv[t], iq[t]);
+                    }
+                    const double qy = __shfl_down_sync(0xffffffffu, iq[t], 1);
+                    const double qz = __shfl_down_sync(0xffffffffu, iq[t], 2);
+                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[t], qy, qz, make_tag(st + 1));
                 }
-                if ((lane & 15) == 0) {
-                    double* dstp = &s_part[pbuf][warp][hi ? 3 : 0];
-                    dstp[0] = k0, dstp[1] = k1, dstp[2] = k2;
-                }
+                cstep[t] = st + 1;
+                pbuf ^= 1;
+                tick(4);
             }
-            tick(1);
-            compute_bar();
-            // (4) threads 0..7: a = half0 + half1; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
-            //     tagged sector {x, y, z, step}: the 8 sectors of the block leave in one store instruction, unfenced
-            if (tid < GB) {
-                if (integ) {
-                    const double* p0 = &s_part[pbuf][tid >> 1][3 * (tid & 1)];
-                    const double* p1 = &s_part[pbuf][4 + (tid >> 1)][3 * (tid & 1)];
+            any = false;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) kick_drift(p0[k] + p1[k], s.v[k], s.q[k]);
-                }
-                double* sec = gbuf + ((size_t)(st & 1) * T + t) * C * GB * 4;
-                st_sector(sec + (size_t)(c * GB + tid) * 4, s.q[0], s.q[1], s.q[2], __longlong_as_double((long long)st));
-            }
-            pbuf ^= 1;
-            tick(2);
+            for (int t = 0; t < T; t++) any |= cact[t];
         }
-        any = false;
+        if (aborted && tid == 0) {
 #pragma unroll
-        for (int t = 0; t < T; t++) any |= ts[t].active;
-    }
+            for (int t = 0; t < T; t++) sh.stop[t] = 1;
+        }
 
-    if (PROFILE && tid == 0 && c == 0) {
-        long long g1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-        for (int k = 0; k < 7; k++) prof[k] = pacc[k];
-        prof[7] = (clock64() - c0) * 1000 / (g1 - g0 > 0 ? g1 - g0 : 1);  // SM MHz over the step loop
-    }
-    // write back
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-        const TrajDesc& d = descs[t];
-        TState& s = ts[t];
-        if (integ) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                d.q[k * n + my_body] = s.q[k];
-                d.v[k * n + my_body] = s.v[k];
+        if (PROFILE) {
+            if (tid == 0 && c == 0) {
+                long long g1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+                for (int k = 0; k < 5; k++) prof[k] = pacc[k];
+                prof[6] = pacc[5];
+                prof[7] = (clock64() - c0) * 1000 / (g1 - g0 > 0 ? g1 - g0 : 1);  // SM MHz over the step loop
             }
         }
-        if (c == 0 && warp == 0) {
-            if (lane < s.n_dev) d.ev->reach_step[lane] = s.my_reach;
-            if (tid == 0) {
-                d.ev->min_d2 = s.min_d2;
-                d.ev->argmin_step = s.argmin_step;
-                d.ev->hit_step = s.hit_step;
-                d.ev->destroyed_step = s.destroyed_step;
-                d.ev->cost = s.cost;
-                d.ev->steps_done = s.step;
-                d.ev->n_reach = s.n_dev;
-                if (s.kind == NB_KIND_Q3 && s.destroyed_step != -2) d.m[s.DD] = 0.0;  // hw5.cu:306
+        if (PROFILE && n_stale) atomicAdd((unsigned long long*)&prof[5], n_stale);
+        // write back
+        if (integ && my_body < n) {
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const TrajDesc& d = descs[t];
+                d.q[ik * n + my_body] = iq[t];
+                d.v[ik * n + my_body] = iv[t];
             }
         }
     }
+    // nobody leaves while a cluster peer may still multicast into its shared memory
+    __syncthreads();
+    cluster_sync_all();
 }
 
 int env_int(const char* name, int dflt) {
@@ -501,47 +644,66 @@ int env_int(const char* name, int dflt) {
 }
 
 int blocks_for(int n) { return (n + GB - 1) / GB; }
-int nchunk_for(int n) { return (blocks_for(n) + 31) / 32; }
-size_t smem_for(int n, int T) { return (size_t)T * 7 * nchunk_for(n) * CHUNK * sizeof(double); }
+int padded_blocks(int n, int cs) { return (blocks_for(n) + cs - 1) / cs * cs; }
+size_t smem_for(int n, int T, int cs) {
+    const size_t R = (size_t)padded_blocks(n, cs) * GB;
+    return (size_t)T * 10 * ((R + RPAD - 1) / RPAD * RPAD) * sizeof(double);
+}
 
 struct WsLayout {
     size_t gbuf_bytes, total;
 };
 WsLayout ws_layout(int n, int T) {
     WsLayout w;
-    const size_t C = blocks_for(n);
-    w.gbuf_bytes = 2 * (size_t)T * C * GB * 4 * sizeof(double);  // [parity][T][C*8] sectors {x, y, z, step tag}
-    w.total = w.gbuf_bytes + 256;
+    const size_t R = (size_t)padded_blocks(n, MAX_CS) * GB;
+    w.gbuf_bytes = 2 * (size_t)T * R * 4 * sizeof(double);  // [parity][T][R] sectors {x, y, z, step tag}
+    w.total = w.gbuf_bytes + 64 + NPROF * sizeof(long long);
     return w;
 }
 
-template <int MATH, int T>
-int launch_t(int n, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
-    const int C = blocks_for(n);
-    const size_t smem = smem_for(n, T);
+template <int MATH, int T, int NJ>
+int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
+    constexpr int GT = 32 * (2 * NJ + 2);
+    const int C = padded_blocks(n, cs);
+    const size_t smem = smem_for(n, T, cs);
     const WsLayout w = ws_layout(n, T);
     double* gbuf = (double*)ws;
     int* status = (int*)((char*)ws + w.gbuf_bytes);
     long long* prof = (long long*)((char*)ws + w.gbuf_bytes + 64);
     static const bool profile = env_int("NB_GRID_PROFILE", 0) != 0;
-    auto kern = (T == 1 && profile) ? grid_traj_kernel<MATH, T, (T == 1)> : grid_traj_kernel<MATH, T, false>;
+    static const int delay_clk_env = env_int("NB_GRID_DELAY", 900);
+    auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true> : grid_traj_kernel<MATH, T, NJ, false>;
     NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cs > 8) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     NB_CUDA(cudaMemsetAsync(ws, 0, w.total, stream));  // tag 0 = no step; also clears status
-    int nchunk = nchunk_for(n);
-    static unsigned poll_sleep_ns = (unsigned)env_int("NB_GRID_POLL_NS", 0);
-    void* args[] = {(void*)&descs, (void*)&fst, (void*)&gbuf, (void*)&prof, (void*)&status, (void*)&nchunk,
-                    (void*)&poll_sleep_ns};
-    NB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(C), dim3(GT), args, smem, stream));
+    int R = C * GB, delay_clk = delay_clk_env;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C), cfg.blockDim = dim3(GT), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = cs, attrs[0].val.clusterDim.y = 1, attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs, cfg.numAttrs = 2;
+    int max_clusters = 0;
+    NB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters < C / cs) {
+        set_error_detail("grid trajectory kernel: " + std::to_string(C / cs) + " clusters of " + std::to_string(cs) +
+                         " blocks are not co-resident on this GPU (max " + std::to_string(max_clusters) + "); set NB_GRID_CS lower");
+        return NB_ERR_UNSUPPORTED;
+    }
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk));
     count_launch();
     int h_status = 0;
     NB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, stream));
     NB_CUDA(cudaStreamSynchronize(stream));
-    if (T == 1 && profile) {
+    if (profile) {
         long long h[8];
         NB_CUDA(cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "grid profile (clk, block 0 thread 0): chunk waits + pairs %lld | observers + device pairs + butterfly %lld | "
-                        "barrier + integrate + publish %lld | SM clock %lld MHz\n",
-                h[0], h[1], h[2], h[7]);
+        fprintf(stderr,
+                "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait copy %lld | validate %lld | pairs %lld | wait observer %lld | "
+                "butterfly %lld | barrier+integrate+publish %lld | stale records polled (all blocks) %lld | SM clock %lld MHz\n",
+                T, NJ, cs, delay_clk, h[0], h[6], h[1], h[2], h[3], h[4], h[5], h[7]);
     }
     if (h_status != 0) {
         set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
@@ -551,54 +713,56 @@ int launch_t(int n, const TrajDesc* descs, const double* fst, void* ws, cudaStre
 }
 
 template <int MATH>
-int launch_m(int T, int n, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
-    switch (T) {
-        case 1: return launch_t<MATH, 1>(n, descs, fst, ws, stream);
-        case 2: return launch_t<MATH, 2>(n, descs, fst, ws, stream);
-        case 3: return launch_t<MATH, 3>(n, descs, fst, ws, stream);
-        default: return launch_t<MATH, 4>(n, descs, fst, ws, stream);
-    }
+int launch_m(int T, int n, int cs, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
+    if (T == 1) return launch_t<MATH, 1, 4>(n, cs, descs, fst, ws, stream);
+    return launch_t<MATH, 2, 4>(n, cs, descs, fst, ws, stream);
+}
+
+// cluster size: NB_GRID_CS (1, 2, 4, 8), default 4; every cluster must be co-resident
+int cluster_size_for(int n) {
+    static const int want = env_int("NB_GRID_CS", 4);
+    int cs = want;
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 4;
+    while (cs > 1 && padded_blocks(n, cs) > 144) cs >>= 1;
+    return cs;
 }
 
 }  // namespace
 
 // the largest group of trajectories one launch takes for this n (shared-memory bound)
-static int group_size(int n) {
-    // measured on B200, b1024: 4 systems per launch fit (224 KiB + 1.3 KiB static) but the T = 4 instantiation
-    // spills and runs the four-trajectory solve in 3.80 s; groups of 3 + 1 take 3.07 s
+static int group_size(int n, int cs) {
     int T = MAX_T;
-    while (T > 1 && smem_for(n, T) > 220 * 1024) T--;
-    return T;
+    while (T > 1 && smem_for(n, T, cs) > 200 * 1024) T--;
+    static const int cap = env_int("NB_GRID_T", MAX_T);
+    return T < cap ? T : (cap < 1 ? 1 : cap);
 }
 
 bool grid_traj_supported(int gpu, int n, int n_traj) {
-    (void)n_traj;
     static const int enabled = env_int("NB_GRID", 1);
     static const int min_n = env_int("NB_GRID_MIN_N", 128);
     if (!enabled || n < min_n || n > NB_MAX_SMALL_N) return false;
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, gpu) != cudaSuccess) return false;
     if (!p.cooperativeLaunch) return false;
-    if (blocks_for(n) > p.multiProcessorCount) return false;
-    if (smem_for(n, 1) > (size_t)p.sharedMemPerBlockOptin) return false;
+    if (padded_blocks(n, cluster_size_for(n)) > p.multiProcessorCount) return false;
+    if (smem_for(n, 1, cluster_size_for(n)) > (size_t)p.sharedMemPerBlockOptin) return false;
     return true;
 }
 
 size_t grid_traj_workspace_bytes(int n, int n_traj) {
-    (void)n_traj;
     return ws_layout(n, MAX_T).total;
 }
 
 int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs, const double* fst, int gpu, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
-    (void)gpu;
     if (ws_bytes < ws_layout(n, MAX_T).total) return NB_ERR_ARG;
-    const int G = group_size(n);
+    // STRICT never comes here: its ascending-j sum is the single-block kernel's (nb_host.cu)
+    if (math != NB_MATH_FAST) return NB_ERR_UNSUPPORTED;
+    const int cs = cluster_size_for(n);
+    const int G = group_size(n, cs);
     for (int t0 = 0; t0 < n_traj; t0 += G) {  // groups of up to G trajectories run in lock step
         const int T = n_traj - t0 < G ? n_traj - t0 : G;
-        // STRICT never comes here: its ascending-j sum is the single-block kernel's (nb_host.cu)
-        if (math != NB_MATH_FAST) return NB_ERR_UNSUPPORTED;
-        int rc = launch_m<MATH_FAST>(T, n, descs + t0, fst, ws, stream);
+        int rc = launch_m<MATH_FAST>(T, n, cs, descs + t0, fst, ws, stream);
         if (rc) return rc;
     }
     return NB_OK;

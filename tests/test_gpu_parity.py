@@ -217,6 +217,13 @@ def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     out = json.loads(r.stdout.decode().strip().split("\n")[-1])
+    # the exchange knobs change timing only, never results: no multicast / clusters of 2, copies issued far too early
+    # (every record stale at first: all of them go through the poll-and-patch path) and one system per launch
+    for knobs in (dict(NB_GRID_CS="1"), dict(NB_GRID_CS="2", NB_GRID_DELAY="0", NB_GRID_T="1")):
+        r2 = subprocess.run([sys.executable, "-c", code.replace("('b100', 'b200', 'b90')", "('b200',)")], capture_output=True,
+                            env=dict(env, **knobs), timeout=600)
+        assert r2.returncode == 0, r2.stderr.decode()[-2000:]
+        assert json.loads(r2.stdout.decode().strip().split("\n")[-1])["b200"] == out["b200"], knobs
     kats = json.load(open(os.path.join(GOLDEN, "oracle_kats.json")))
     for case, o in out.items():
         g = golden_lines(case)

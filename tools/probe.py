@@ -33,6 +33,20 @@ def traj(case="b1024", steps=2000):
         t.close()
 
 
+def trajrep(case="b1024", steps=100000, reps=6):
+    """Step latency of one trajectory, repeated (fresh trajectory each time): run-to-run spread of the grid kernel."""
+    s = nb.read_input(os.path.join(G, case + ".in"))
+    steps, out = int(steps), []
+    for _ in range(int(reps)):
+        t = nb.Trajectory(s, nb.KIND_Q1)
+        t.run(10)
+        t0 = time.time()
+        t.run(10 + steps)
+        out.append((time.time() - t0) / steps * 1e6)
+        t.close()
+    print("%s us/step over %d reps of %d steps: %s | min %.2f max %.2f" % (case, len(out), steps, " ".join("%.2f" % x for x in out), min(out), max(out)), flush=True)
+
+
 def ens(S=148, steps=300, case="b1024"):
     S, steps = int(S), int(steps)
     s = nb.read_input(os.path.join(G, case + ".in"))

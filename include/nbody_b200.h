@@ -157,6 +157,14 @@ int nb_read_input(const char* path, int max_n, int* n, int* planet, int* asteroi
                   double* v, double* m, unsigned char* is_device);
 int nb_write_output(const char* path, double min_dist, int hit_time_step, int gravity_device_id,
                     double missile_cost);
+/* The input format, written (17 significant digits): generated / advanced systems can go through hw5, nbtool and
+ * the reference's samples/nbody.cc alike.  SURVEY.md 8f rank 4. */
+int nb_write_input(const char* path, int n, int planet, int asteroid, const double* q, const double* v,
+                   const double* m, const unsigned char* is_device);
+/* Synthetic system of SURVEY.md 8d config C5 (std::mt19937_64(seed)): body 0 = planet, 1 = asteroid, the last
+ * n_devices bodies are gravity devices.  q, v: [3n] planar; m, is_device: [n]. */
+int nb_generate_system(int n, unsigned long long seed, int n_devices, double* q, double* v, double* m,
+                       unsigned char* is_device, int* planet, int* asteroid);
 /* the whole CLI: hw5 <input> <output> (hw5.cu:532-616) */
 int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus);
 

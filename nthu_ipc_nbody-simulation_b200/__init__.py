@@ -18,6 +18,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnbody_b200.so")
+NBTOOL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nbtool")
 HW5_PATH = os.path.join(_HERE, "hw5")
 
 NB_OK = 0
@@ -67,7 +68,7 @@ ABI_SYMBOLS = [
     "nb_version", "nb_strerror", "nb_last_error_detail", "nb_device_count", "nb_kernel_launches",
     "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_fork_on", "nb_traj_destroy",
     "nb_ensemble_run", "nb_solve", "nb_solve_trajectory_count", "nb_solve_partial", "nb_solve_combine",
-    "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_hw5_main",
+    "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_write_input", "nb_generate_system", "nb_hw5_main",
     "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_large_step_p2p", "nb_large_blocks_per_step", "nb_large_p2p_counter_bytes", "nb_large_wait_p2p",
     "nb_dev_alloc", "nb_dev_free", "nb_dev_copy", "nb_ipc_export", "nb_ipc_open", "nb_ipc_close", "nb_fp64_peak", "nb_fp64_peak_variant",
 ]
@@ -113,6 +114,8 @@ def lib():
     L.nb_read_input.argtypes = [C.c_char_p, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, _up]
     L.nb_write_output.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_double]
     L.nb_hw5_main.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.nb_write_input.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _up]
+    L.nb_generate_system.argtypes = [C.c_int, C.c_ulonglong, C.c_int, _dp, _dp, _dp, _up, _ip, _ip]
     L.nb_large_scratch_bytes.restype = C.c_longlong
     L.nb_large_scratch_bytes.argtypes = [C.c_int, C.c_int]
     L.nb_large_pack.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -205,6 +208,22 @@ def read_input(path):
     dev = np.zeros(nn, dtype=np.uint8)
     _check(lib().nb_read_input(os.fsencode(path), nn, C.byref(n), C.byref(p), C.byref(a), _d(q), _d(v), _d(m), _u(dev)))
     return System(nn, p.value, a.value, q, v, m, dev)
+
+
+def write_input(path, s):
+    """The reference's input format (nbody.cc:22-39), written with 17 significant digits."""
+    _check(lib().nb_write_input(os.fsencode(path), s.n, s.planet, s.asteroid, _d(s.q), _d(s.v), _d(s.m), _u(s.is_device)))
+
+
+def generate_system(n, seed=42, n_devices=4):
+    """SURVEY.md 8d config C5 (std::mt19937_64(seed) in the library, same as `nbtool gen n seed out.in`): positions
+    uniform in a cube of side 1e13 m centred at (-2.0e20, -2.9e20, 1.8e18), velocities N(0, (1e7 m/s)^2), masses
+    log-uniform in [1e20, 1e30] kg, body 0 = planet, body 1 = asteroid, the last n_devices bodies gravity devices."""
+    q, v, m = np.empty(3 * n), np.empty(3 * n), np.empty(n)
+    dev = np.zeros(n, dtype=np.uint8)
+    p, a = C.c_int(), C.c_int()
+    _check(lib().nb_generate_system(n, seed, n_devices, _d(q), _d(v), _d(m), _u(dev), C.byref(p), C.byref(a)))
+    return System(n, p.value, a.value, q, v, m, dev)
 
 
 def write_output(path, min_dist, hit_time_step, gravity_device_id, missile_cost):

@@ -11,7 +11,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -116,6 +118,53 @@ int nb_write_output(const char* path, double min_dist, int hit_time_step, int gr
     }
     int k = fprintf(f, "%.16e\n%d\n%d %.16e\n", min_dist, hit_time_step, gravity_device_id, missile_cost);
     if (fclose(f) != 0 || k < 0) return NB_ERR_IO;
+    return NB_OK;
+}
+
+// The input format, written: lets a generated or advanced system go through `hw5`, `nbtool` and the reference's own
+// samples/nbody.cc alike.  17 significant digits (%.16e) round-trip every double through strtod / operator>>.
+int nb_write_input(const char* path, int n, int planet, int asteroid, const double* q, const double* v, const double* m,
+                   const unsigned char* is_device) {
+    if (!path || n < 1 || !q || !v || !m || !is_device) return NB_ERR_ARG;
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        nb::set_error_detail(std::string("cannot write ") + path);
+        return NB_ERR_IO;
+    }
+    bool ok = fprintf(f, "%d %d %d\n", n, planet, asteroid) > 0;
+    for (int i = 0; i < n && ok; i++) {
+        const char* type = is_device[i] ? "device" : i == planet ? "planet" : i == asteroid ? "asteroid" : "star";
+        ok = fprintf(f, "%.16e %.16e %.16e %.16e %.16e %.16e %.16e %s\n", q[i], q[i + n], q[i + 2 * n], v[i], v[i + n],
+                     v[i + 2 * n], m[i], type) > 0;
+    }
+    if (fclose(f) != 0 || !ok) return NB_ERR_IO;
+    return NB_OK;
+}
+
+// Synthetic system of SURVEY.md 8d, config C5: positions uniform in a cube of side 1e13 m centred at
+// (-2.0e20, -2.9e20, 1.8e18) (the goldens' neighbourhood), velocities N(0, (1e7 m/s)^2) per component, masses
+// log-uniform in [1e20, 1e30] kg, body 0 = planet, body 1 = asteroid, the last n_devices bodies = gravity devices.
+// std::mt19937_64 raw output (standardised) with our own transforms (the std:: distributions are not), so the same
+// (n, seed) gives the same system wherever libm's log/cos/pow agree.
+int nb_generate_system(int n, unsigned long long seed, int n_devices, double* q, double* v, double* m,
+                       unsigned char* is_device, int* planet, int* asteroid) {
+    if (n < 2 || n_devices < 0 || n_devices > NB_MAX_DEVICES || !q || !v || !m || !is_device || !planet || !asteroid)
+        return NB_ERR_ARG;
+    std::mt19937_64 rng(seed);
+    auto uni = [&]() { return (double)(rng() >> 11) * (1.0 / 9007199254740992.0); };  // [0, 1)
+    const double centre[3] = {-2.0e20, -2.9e20, 1.8e18};
+    for (int c = 0; c < 3; c++)
+        for (int i = 0; i < n; i++) q[(size_t)c * n + i] = centre[c] + (uni() - 0.5) * 1e13;
+    for (size_t k = 0; k < 3 * (size_t)n; k += 2) {  // Box-Muller, both variates used
+        const double u1 = 1.0 - uni(), u2 = uni();   // u1 in (0, 1]
+        const double r = sqrt(-2.0 * log(u1)) * 1e7, a = 6.283185307179586476925286766559 * u2;
+        v[k] = r * cos(a);
+        if (k + 1 < 3 * (size_t)n) v[k + 1] = r * sin(a);
+    }
+    for (int i = 0; i < n; i++) m[i] = pow(10.0, 20.0 + 10.0 * uni());
+    const int first_dev = n - n_devices < 2 ? 2 : n - n_devices;
+    for (int i = 0; i < n; i++) is_device[i] = i >= first_dev ? 1 : 0;
+    *planet = 0, *asteroid = 1;
     return NB_OK;
 }
 

@@ -27,21 +27,11 @@ def partition(n, world, rank):
 
 
 def synthetic_system(n, seed=42):
-    """positions uniform in a cube of side 1e13 m centred at
-    (-2.0e20, -2.9e20, 1.8e18), velocities N(0, (1e7 m/s)^2), masses log-uniform in [1e20, 1e30] kg,
-    body 0 = planet, body 1 = asteroid, the last 4 bodies are gravity devices."""
-    from . import System
+    """SURVEY.md §8d config C5 through the library's generator (`nb_generate_system`, the one `nbtool gen` uses):
+    body 0 = planet, body 1 = asteroid, the last 4 bodies (fewer for tiny n) are gravity devices."""
+    from . import generate_system
 
-    rng = np.random.default_rng(seed)
-    centre = np.array([-2.0e20, -2.9e20, 1.8e18])
-    q = np.empty(3 * n)
-    for c in range(3):
-        q[c * n:(c + 1) * n] = centre[c] + (rng.random(n) - 0.5) * 1e13
-    v = rng.normal(0.0, 1e7, 3 * n)
-    m = 10.0 ** rng.uniform(20.0, 30.0, n)
-    dev = np.zeros(n, dtype=np.uint8)
-    dev[max(2, n - 4):] = 1
-    return System(n, 0, 1, q, v, m, dev)
+    return generate_system(n, seed, min(4, max(0, n - 2)))
 
 
 def fst(step):

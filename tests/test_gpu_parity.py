@@ -236,6 +236,38 @@ def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
         assert o["q3"] == [d["q3_hit_step"] for d in k["devices"]]
 
 
+# ---- nbtool: generator / ensembles / state files from the command line -----------------------
+def test_nbtool_ensemble_and_advance(nb, oracle, tmp_path):
+    """`nbtool ensemble` = config C4's members (velocities scaled by 1 + 1e-9 k) through nb_ensemble_run over the visible
+    GPUs; `nbtool advance` = run_step x steps with the state written in the reference's input format."""
+    out = tmp_path / "ens.txt"
+    subprocess.check_call([nb.NBTOOL_PATH, "ensemble", case_path("b100"), "5", "2000", str(out)])
+    rows = [l.split() for l in out.read_text().strip().split("\n")]
+    assert [int(r[0]) for r in rows] == [0, 1, 2, 3, 4]
+    s = nb.read_input(case_path("b100"))
+    for k in (0, 3):
+        t = nb.Trajectory(nb.System(s.n, s.planet, s.asteroid, s.q, s.v * (1 + 1e-9 * k), s.m, s.is_device), nb.KIND_Q2)
+        ev = t.run(2000)
+        t.close()
+        assert float(rows[k][1]) == float("%.16e" % np.sqrt(ev.min_d2)) and int(rows[k][2]) == ev.argmin_step and int(rows[k][3]) == ev.hit_step
+    lst = tmp_path / "list.txt"
+    lst.write_text("# two goldens of the same n would go here\n%s\n%s\n" % (case_path("b100"), case_path("b100")))
+    out2 = tmp_path / "ens2.txt"
+    subprocess.check_call([nb.NBTOOL_PATH, "ensemble-list", str(lst), "2000", str(out2)])
+    rows2 = [l.split() for l in out2.read_text().strip().split("\n")]
+    assert rows2[0][1:] == rows[0][1:] and rows2[1][1:] == rows[0][1:]
+    adv = tmp_path / "adv.in"
+    subprocess.check_call([nb.NBTOOL_PATH, "advance", case_path("b50"), "500", str(adv)])
+    a = nb.read_input(str(adv))
+    s = nb.read_input(case_path("b50"))
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 500, s.n, q, v, s.m, s.is_device)
+    assert np.array_equal(a.q, q) and np.array_equal(a.v, v)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 0, 500)
+    assert np.max(np.abs(a.q - qo) / np.abs(qo)) < 1e-15  # FAST kernel vs oracle after 500 steps
+
+
 # ---- ensembles ---------------------------------------------------------------------------------------
 def test_ensemble_members_match_individual_runs(nb, oracle):
     """SURVEY §8d config C4 in miniature: member k = the golden system with velocities scaled by (1 + 1e-9 k)."""

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbody_b200.so")
+LIB_PATH = os.environ.get("NB_LIB_PATH") or os.path.join(_HERE, "libnbody_b200.so")  # NB_LIB_PATH: A/B builds of the library
 NBTOOL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nbtool")
 HW5_PATH = os.path.join(_HERE, "hw5")
 

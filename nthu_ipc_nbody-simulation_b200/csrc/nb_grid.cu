@@ -176,6 +176,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     auto s_gm = [&](int t, int stage) { return smem + (size_t)t * 10 * RS + 8 * RS + (size_t)stage * RS; };
     auto g_rec = [&](int t, int st) { return gbuf + ((size_t)(st & 1) * T + t) * (size_t)R * 4; };
 
+    if (PROFILE && tid == 0) {  // globaltimer (ns) at block entry: prof[8] = min, prof[9] = max over blocks
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMin((unsigned long long*)&prof[8], g);
+        atomicMax((unsigned long long*)&prof[9], g);
+    }
     if (tid == 0) {
         sh.abort = 0;
 #pragma unroll
@@ -633,6 +639,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             }
         }
     }
+    if (PROFILE && tid == 0) {  // globaltimer at the end of this block's work: prof[10] = min, prof[11] = max
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        atomicMin((unsigned long long*)&prof[10], g);
+        atomicMax((unsigned long long*)&prof[11], g);
+    }
     // nobody leaves while a cluster peer may still multicast into its shared memory
     __syncthreads();
     cluster_sync_all();
@@ -680,6 +692,15 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cs > 8) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     NB_CUDA(cudaMemsetAsync(ws, 0, w.total, stream));  // tag 0 = no step; also clears status
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (profile) {
+        const unsigned long long big = ~0ULL;
+        NB_CUDA(cudaMemcpyAsync(prof + 8, &big, 8, cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaMemcpyAsync(prof + 10, &big, 8, cudaMemcpyHostToDevice, stream));
+        NB_CUDA(cudaEventCreate(&pe0));
+        NB_CUDA(cudaEventCreate(&pe1));
+        NB_CUDA(cudaEventRecord(pe0, stream));
+    }
     int R = C * GB, delay_clk = delay_clk_env;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C), cfg.blockDim = dim3(GT), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
@@ -698,12 +719,18 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     }
     NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk));
     count_launch();
+    if (profile) NB_CUDA(cudaEventRecord(pe1, stream));
     int h_status = 0;
     NB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, stream));
     NB_CUDA(cudaStreamSynchronize(stream));
     if (profile) {
-        long long h[8];
+        long long h[12];
         NB_CUDA(cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost));
+        float kms = 0;
+        NB_CUDA(cudaEventElapsedTime(&kms, pe0, pe1));
+        cudaEventDestroy(pe0), cudaEventDestroy(pe1);
+        fprintf(stderr, "grid kernel %.3f ms by events | block entry spread %.1f us | first entry -> last block done %.3f ms | block done spread %.1f us\n",
+                kms, (h[9] - h[8]) * 1e-3, (h[11] - h[8]) * 1e-6, (h[11] - h[10]) * 1e-3);
         fprintf(stderr,
                 "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait copy %lld | validate %lld | pairs %lld | wait observer %lld | "
                 "butterfly %lld | barrier+integrate+publish %lld | stale records polled (all blocks) %lld | SM clock %lld MHz\n",

@@ -143,8 +143,8 @@ struct Shared {
     // the bytes); obs: the observer has judged the step (1 arrival).  Each completes once per two steps.
     alignas(8) uint64_t full[MAX_T][2];
     alignas(8) uint64_t obs[MAX_T][2];
+    alignas(8) uint64_t trig[MAX_T][2];  // producer trigger: this block's sums of the step are complete (1 arrival)
     volatile int flags[MAX_T][2];   // FLAG_* of the step held by the stage, valid once obs completed
-    volatile int pubstep[MAX_T];    // the step whose partial sums are complete in this block (producer trigger)
     volatile int stop[MAX_T];
     volatile int abort;
     double part[2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part
@@ -188,10 +188,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         for (int t = 0; t < T; t++) {
             // a trajectory that stopped in an earlier launch never steps again
             sh.stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
-            sh.pubstep[t] = descs[t].step_begin;
             for (int b = 0; b < 2; b++) {
                 mbar_init(&sh.full[t][b], 1);
                 mbar_init(&sh.obs[t][b], 1);
+                mbar_init(&sh.trig[t][b], 1);
                 sh.flags[t][b] = 0;
             }
         }
@@ -292,21 +292,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 for (int t = 0; t < T; t++) {
                     if (!pact[t]) continue;
                     const int st = pstep[t] + 1;
-                    // this block's sums of step st are complete: it publishes within ~150 clk, and so does everybody
-                    const long long t0 = clock64();
-                    bool go = true;
-                    while (sh.pubstep[t] < st) {
-                        if (sh.stop[t] || sh.abort) {
-                            go = false;
-                            break;
-                        }
-                        if (clock64() - t0 > SPIN_LIMIT) {
-                            sh.abort = 1;
-                            atomicExch(status, 1);
-                            go = false;
-                            break;
-                        }
-                    }
+                    // wait (hardware-suspended on the mbarrier, no issue slots taken from the compute warps) until this
+                    // block's sums of step st are complete: it publishes within ~150 clk, and so does everybody
+                    bool go = wait_bar(&sh.trig[t][st & 1], (uint32_t)((st - descs[t].step_begin - 1) >> 1) & 1u);
+                    if (sh.stop[t]) go = false;
                     if (!go) {
                         pact[t] = false;
                         continue;
@@ -552,7 +541,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 tick(2);
                 if (flags & FLAG_STOP) {
                     cact[t] = false;
-                    if (tid == 0) sh.stop[t] = 1;  // releases the producer
+                    if (tid == 0) {  // releases the producer, which waits for the trigger of step st + 1
+                        sh.stop[t] = 1;
+                        __threadfence_block();
+                        mbar_arrive(&sh.trig[t][(st + 1) & 1]);
+                    }
                     continue;
                 }
                 // (3) transposing butterfly: 12 sums -> lanes 0/8/16/24 hold body 0/1/2/3
@@ -594,7 +587,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
                 //     tagged sector {x, y, z, step}, unfenced
                 if (warp == 0) {
-                    if (lane == 0) sh.pubstep[t] = st + 1;  // producer trigger: everybody publishes within ~150 clk
+                    if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
                     if (integ) {
                         const double* p = &sh.part[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
                         double a = p[0];

@@ -32,6 +32,7 @@ extern "C" {
 
 /* arithmetic of the pair term (nbody.cc:65-72) */
 #define NB_MATH_FAST 0   /* FMA r^2, rsqrt seed + cubic correction (<= 2^-52 rel.), FMA accumulate, j split over lanes */
+#define NB_SOLVE_ALL_DEVICES 0x100 /* OR into `math` of nb_solve / nb_solve_partial: simulate every device's query-3 trajectory from step 0 (diagnostics for all devices) instead of stopping at the cheapest saviour */
 #define NB_MATH_STRICT 1 /* IEEE only: sqrt(r2*r2*r2), ((G*mj)*d)/dist3, no FMA, ascending j (== hw5.cu:200-203 form of nbody.cc) */
 
 /* trajectory kinds = the observers that run after every step */

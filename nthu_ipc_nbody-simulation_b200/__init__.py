@@ -24,6 +24,7 @@ HW5_PATH = os.path.join(_HERE, "hw5")
 NB_OK = 0
 NB_ERR_ARG, NB_ERR_CUDA, NB_ERR_NO_GPU, NB_ERR_UNSUPPORTED, NB_ERR_IO = -1, -2, -3, -4, -5
 MATH_FAST, MATH_STRICT = 0, 1
+SOLVE_ALL_DEVICES = 0x100  # OR into math: every device's query-3 trajectory from step 0 (NB_SOLVE_ALL_DEVICES)
 KIND_PLAIN, KIND_Q1, KIND_Q2, KIND_Q3 = 0, 1, 2, 3
 MAX_DEVICES = 64
 MAX_SMALL_N = 1024
@@ -302,8 +303,12 @@ def ensemble_run(q, v, m, is_device, planet, asteroid, kind=KIND_PLAIN, destroy_
     return list(ev), secs.value
 
 
-def solve(system, gpus=None, n_steps=N_STEPS, math=MATH_FAST):
-    """The three problems of main() (nbody.cc:106-143, hw5.cu:563-606) -> NbAnswer."""
+def solve(system, gpus=None, n_steps=N_STEPS, math=MATH_FAST, all_devices=False):
+    """The three problems of main() (nbody.cc:106-143, hw5.cu:563-606) -> NbAnswer.  With fewer GPUs than trajectories
+    the scheduler forks query 3 from query 2 and stops at the cheapest saving device (q3_hit_step == -3 for devices it
+    did not need to simulate); all_devices=True simulates every device's trajectory from step 0."""
+    if all_devices:
+        math |= SOLVE_ALL_DEVICES
     if gpus is None:
         gpus = [0]
     if isinstance(gpus, int):
@@ -315,9 +320,11 @@ def solve(system, gpus=None, n_steps=N_STEPS, math=MATH_FAST):
     return ans
 
 
-def solve_partial(system, gpu, part, n_parts, n_steps=N_STEPS, math=MATH_FAST):
-    """This part's share of the trajectories (t % n_parts == part) on `gpu`.
-    Returns (events array with this part's entries filled, gpu_seconds, pair_interactions)."""
+def solve_partial(system, gpu, part, n_parts, n_steps=N_STEPS, math=MATH_FAST, all_devices=False):
+    """This part's share of the trajectories on `gpu` (the library's scheduler decides which: nb_host.cu).
+    Returns (events array: this part's entries filled, the others marked steps_done == -2; gpu_seconds; pair_interactions)."""
+    if all_devices:
+        math |= SOLVE_ALL_DEVICES
     cs = system._c()
     cnt = C.c_int()
     _check(lib().nb_solve_trajectory_count(C.byref(cs), C.byref(cnt)))
@@ -334,12 +341,12 @@ def solve_combine(system, evs):
     return ans
 
 
-def solve_distributed(system, rank, world, gpu, n_steps=N_STEPS, math=MATH_FAST, group=None):
+def solve_distributed(system, rank, world, gpu, n_steps=N_STEPS, math=MATH_FAST, group=None, all_devices=False):
     """One process per GPU (torchrun): every rank simulates its share of the trajectories, the
     nb_events structs (a few hundred bytes each) are gathered with torch.distributed — the path has
     no data-path collective — and every rank applies the selection rule.  Returns (answer,
     max gpu_seconds over ranks, total pair interactions)."""
-    evs, secs, pairs = solve_partial(system, gpu, rank, world, n_steps, math)
+    evs, secs, pairs = solve_partial(system, gpu, rank, world, n_steps, math, all_devices)
     if world > 1:
         import torch.distributed as dist
 
@@ -349,8 +356,9 @@ def solve_distributed(system, rank, world, gpu, n_steps=N_STEPS, math=MATH_FAST,
         merged = (NbEvents * T)()
         for r, (b, s_r, p_r) in enumerate(blobs):
             part = (NbEvents * T).from_buffer_copy(b)
-            for t in range(r, T, world):
-                merged[t] = part[t]
+            for t in range(T):
+                if part[t].steps_done != -2:  # -2 = another part's trajectory
+                    merged[t] = part[t]
         evs = merged
         secs = max(b[1] for b in blobs)
         pairs = sum(b[2] for b in blobs)

@@ -56,7 +56,12 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <string>
+#include <tuple>
 
 #include "nb_internal.h"
 #include "nb_math.cuh"
@@ -163,7 +168,7 @@ struct ObsState {  // per system, observer warp
 template <int MATH, int T, int NJ, bool PROFILE>
 __global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk) {
+                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single) {
     extern __shared__ __align__(128) double smem[];
     __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,7 +311,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     // Copy delay after the trigger: long enough for everybody's sectors of this step to be in the L2 when the
                     // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
                     // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
-                    while (clock64() - t1 < delay_clk) {
+                    int dl = delay_clk;
+                    if (T > 1) {  // the only system still running in this launch waits for every copy: shortest delay
+                        int n_act = 0;
+#pragma unroll
+                        for (int u = 0; u < T; u++) n_act += pact[u] ? 1 : 0;
+                        if (n_act == 1) dl = delay_single;
+                    }
+                    while (clock64() - t1 < dl) {
                     }
                     double* dst = s_pos(t, st & 1) + (size_t)rank * slice * 4;
                     const double* src = g_rec(t, st) + (size_t)rank * slice * 4;
@@ -671,7 +683,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     constexpr int GT = 32 * (2 * NJ + 2);
     const int C = padded_blocks(n, cs);
     const size_t smem = smem_for(n, T, cs);
-    const WsLayout w = ws_layout(n, T);
+    const WsLayout w = ws_layout(n, MAX_T);  // one layout for every T: the status word has a fixed place
     double* gbuf = (double*)ws;
     int* status = (int*)((char*)ws + w.gbuf_bytes);
     long long* prof = (long long*)((char*)ws + w.gbuf_bytes + 64);
@@ -681,10 +693,10 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     // behind the pair loop of the other and a longer delay (fewer stale records, fewer polls) wins (measured: b1024
     // four-trajectory solve on one GPU 2.33 s at 900, 2.00 s at 2600)
     static const int delay_clk_env = env_int("NB_GRID_DELAY", T == 1 ? 900 : 2600);
+    static const int delay_single_env = env_int("NB_GRID_DELAY", 900);
     auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true> : grid_traj_kernel<MATH, T, NJ, false>;
-    NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (cs > 8) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    NB_CUDA(cudaMemsetAsync(ws, 0, w.total, stream));  // tag 0 = no step; also clears status
+    NB_CUDA(cudaMemsetAsync(ws, 0, w.gbuf_bytes, stream));  // tag 0 = no step
+    if (profile) NB_CUDA(cudaMemsetAsync(prof, 0, NPROF * sizeof(long long), stream));
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) {
         const unsigned long long big = ~0ULL;
@@ -694,7 +706,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         NB_CUDA(cudaEventCreate(&pe1));
         NB_CUDA(cudaEventRecord(pe0, stream));
     }
-    int R = C * GB, delay_clk = delay_clk_env;
+    int R = C * GB, delay_clk = delay_clk_env, delay_single = delay_single_env;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C), cfg.blockDim = dim3(GT), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute attrs[2];
@@ -703,20 +715,40 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     attrs[1].id = cudaLaunchAttributeCooperative;
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs, cfg.numAttrs = 2;
-    int max_clusters = 0;
-    NB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-    if (max_clusters < C / cs) {
-        set_error_detail("grid trajectory kernel: " + std::to_string(C / cs) + " clusters of " + std::to_string(cs) +
-                         " blocks are not co-resident on this GPU (max " + std::to_string(max_clusters) + "); set NB_GRID_CS lower");
-        return NB_ERR_UNSUPPORTED;
+    {   // function attributes and the co-residency check: once per (device, kernel, shape) - the chain plan of
+        // nb_solve launches this kernel every NB_SOLVE_CHUNK steps
+        static std::mutex mu;
+        static std::set<std::tuple<int, const void*, size_t, int, int>> checked;
+        int dev = 0;
+        NB_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        const auto key = std::make_tuple(dev, (const void*)kern, smem, cs, C);
+        if (!checked.count(key)) {
+            NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (cs > 8) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            int max_clusters = 0;
+            NB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            if (max_clusters < C / cs) {
+                set_error_detail("grid trajectory kernel: " + std::to_string(C / cs) + " clusters of " + std::to_string(cs) +
+                                 " blocks are not co-resident on this GPU (max " + std::to_string(max_clusters) +
+                                 "); set NB_GRID_CS lower");
+                return NB_ERR_UNSUPPORTED;
+            }
+            checked.insert(key);
+        }
     }
-    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk));
+    const auto h0 = std::chrono::steady_clock::now();
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single));
     count_launch();
-    if (profile) NB_CUDA(cudaEventRecord(pe1, stream));
-    int h_status = 0;
-    NB_CUDA(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    NB_CUDA(cudaStreamSynchronize(stream));
+    {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        static const bool verbose = getenv("NB_VERBOSE") != nullptr;
+        if (verbose && ms > 2.0) fprintf(stderr, "nbody_b200:   cudaLaunchKernelEx took %.1f ms on the host\n", ms);
+    }
+    // asynchronous: the caller synchronises the stream and then reads the sticky status word (grid_traj_status)
     if (profile) {
+        NB_CUDA(cudaEventRecord(pe1, stream));
+        NB_CUDA(cudaStreamSynchronize(stream));
         long long h[12];
         NB_CUDA(cudaMemcpy(h, prof, sizeof h, cudaMemcpyDeviceToHost));
         float kms = 0;
@@ -728,10 +760,6 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
                 "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait copy %lld | validate %lld | pairs %lld | wait observer %lld | "
                 "butterfly %lld | barrier+integrate+publish %lld | stale records polled (all blocks) %lld | SM clock %lld MHz\n",
                 T, NJ, cs, delay_clk, h[0], h[6], h[1], h[2], h[3], h[4], h[5], h[7]);
-    }
-    if (h_status != 0) {
-        set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
-        return NB_ERR_CUDA;
     }
     return NB_OK;
 }
@@ -765,13 +793,35 @@ bool grid_traj_supported(int gpu, int n, int n_traj) {
     static const int enabled = env_int("NB_GRID", 1);
     static const int min_n = env_int("NB_GRID_MIN_N", 128);
     if (!enabled || n < min_n || n > NB_MAX_SMALL_N) return false;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, gpu) != cudaSuccess) return false;
-    if (!p.cooperativeLaunch) return false;
-    if (padded_blocks(n, cluster_size_for(n)) > p.multiProcessorCount) return false;
-    if (smem_for(n, 1, cluster_size_for(n)) > (size_t)p.sharedMemPerBlockOptin) return false;
+    // three attributes, cached per device: this runs before every launch and cudaGetDeviceProperties costs 2-200 ms
+    // a call on the B200 boxes (it was the whole "slow launch" of the chunked chain plan)
+    struct Caps {
+        int coop = -1, sms = 0, smem_optin = 0;
+    };
+    static std::mutex mu;
+    static Caps caps[64];
+    if (gpu < 0 || gpu >= 64) return false;
+    Caps c;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (caps[gpu].coop < 0) {
+            Caps q;
+            if (cudaDeviceGetAttribute(&q.coop, cudaDevAttrCooperativeLaunch, gpu) != cudaSuccess ||
+                cudaDeviceGetAttribute(&q.sms, cudaDevAttrMultiProcessorCount, gpu) != cudaSuccess ||
+                cudaDeviceGetAttribute(&q.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, gpu) != cudaSuccess)
+                return false;
+            caps[gpu] = q;
+        }
+        c = caps[gpu];
+    }
+    if (!c.coop) return false;
+    if (padded_blocks(n, cluster_size_for(n)) > c.sms) return false;
+    if (smem_for(n, 1, cluster_size_for(n)) > (size_t)c.smem_optin) return false;
     return true;
 }
+
+// device address of the status word of a workspace: 0 = ok, 1 = an exchange spin timed out (read after the stream is idle)
+const int* grid_traj_status(const void* ws, int n) { return (const int*)((const char*)ws + ws_layout(n, MAX_T).gbuf_bytes); }
 
 size_t grid_traj_workspace_bytes(int n, int n_traj) {
     return ws_layout(n, MAX_T).total;
@@ -784,6 +834,7 @@ int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs, const d
     if (math != NB_MATH_FAST) return NB_ERR_UNSUPPORTED;
     const int cs = cluster_size_for(n);
     const int G = group_size(n, cs);
+    NB_CUDA(cudaMemsetAsync((char*)ws + ws_layout(n, MAX_T).gbuf_bytes, 0, 64, stream));  // status word, sticky over the groups
     for (int t0 = 0; t0 < n_traj; t0 += G) {  // groups of up to G trajectories run in lock step
         const int T = n_traj - t0 < G ? n_traj - t0 : G;
         int rc = launch_m<MATH_FAST>(T, n, cs, descs + t0, fst, ws, stream);

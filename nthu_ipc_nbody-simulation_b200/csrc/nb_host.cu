@@ -2,6 +2,7 @@
 // driver and its ensemble scheduler.  Host code is C++ in the .cu translation unit, as the
 // reference's is (hw5.cu:311-616); the kernels live in nb_traj.cu / nb_grid.cu / nb_large.cu.
 #include <atomic>
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -196,9 +197,11 @@ struct DeviceBatch {
         NB_CUDA(cudaSetDevice(gpu));
         NB_CUDA(cudaMemcpyAsync(descs, h_descs.data(), S * sizeof(TrajDesc), cudaMemcpyHostToDevice, stream));
         NB_CUDA(cudaEventRecord(e0, stream));
+        const auto h0 = std::chrono::steady_clock::now();
         int max_dev = 0;
         for (int s = 0; s < S; s++) max_dev = h_descs[s].n_dev > max_dev ? h_descs[s].n_dev : max_dev;
         // the grid kernel keeps one device per lane; STRICT needs the single block's ascending-j sum
+        bool grid = false;
         if (allow_grid && math == NB_MATH_FAST && max_dev <= 32 && grid_traj_supported(gpu, n, S)) {
             size_t need = grid_traj_workspace_bytes(n, S);
             if (need > grid_ws_bytes) {
@@ -207,13 +210,31 @@ struct DeviceBatch {
                 grid_ws_bytes = need;
             }
             rc = launch_grid_traj(math, n, S, descs, fst, gpu, grid_ws, grid_ws_bytes, stream);
+            grid = true;
         } else {
             rc = launch_traj_batch(math, n, S, descs, fst, stream);
         }
         if (rc) return rc;
-        NB_CUDA(cudaEventRecord(e1, stream));
+        NB_CUDA(cudaEventRecord(e1, stream));  // e0 .. e1 = the kernels only: nothing below waits on the host in between
+        {
+            const double hms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+            static const bool verbose = getenv("NB_VERBOSE") != nullptr;
+            if (verbose && hms > 2.0) fprintf(stderr, "nbody_b200:   host spent %.1f ms between the two event records\n", hms);
+        }
         NB_CUDA(cudaMemcpyAsync(h_ev.data(), ev, S * sizeof(nb_events), cudaMemcpyDeviceToHost, stream));
-        NB_CUDA(cudaStreamSynchronize(stream));
+        int grid_status = 0;
+        if (grid) NB_CUDA(cudaMemcpyAsync(&grid_status, grid_traj_status(grid_ws, n), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        // Busy-wait instead of cudaStreamSynchronize: the blocking wait costs tens of milliseconds of wake-up latency now
+        // and then (measured on the B200 boxes), and the chain plan of nb_solve comes through here every few thousand steps.
+        for (;;) {
+            cudaError_t qe = cudaStreamQuery(stream);
+            if (qe == cudaSuccess) break;
+            if (qe != cudaErrorNotReady) return cuda_fail(qe, "cudaStreamQuery", __FILE__, __LINE__);
+        }
+        if (grid_status != 0) {
+            set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
+            return NB_ERR_CUDA;
+        }
         float ms = 0;
         NB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         gpu_seconds += ms * 1e-3;
@@ -421,11 +442,24 @@ int nb_run_steps(int gpu, int math, int n, double* q, double* v, const double* m
 }
 
 // ---- the three queries -------------------------------------------------------------------------------
-// Ensemble scheduler: Q1, Q2 and one Q3 trajectory per device are independent (each Q3 trajectory is
-// re-simulated from step 0 with identical arithmetic, so its prefix equals Q2's: no snapshot
-// transport, no dependency on Q2 — SURVEY §7.2).  Trajectory t goes to part t % n_parts; each part
-// runs its share as ONE launch on its GPU; no collective, only nb_events structs come back.
-//   trajectory 0 = Q1, 1 = Q2, 2+k = Q3 with device k destroyed.
+// Ensemble scheduler.  trajectory 0 = Q1, 1 = Q2, 2+k = Q3 with device k destroyed.  Two plans, no collective in
+// either, only nb_events structs come back:
+//   * INDEPENDENT (as many GPUs as trajectories, or NB_SOLVE_ALL_DEVICES): Q1, Q2 and one Q3 trajectory per device
+//     are all simulated from step 0 (identical arithmetic gives each Q3 trajectory Q2's prefix: no snapshot
+//     transport, no dependency on Q2 - SURVEY 7.2); trajectory t goes to part t % n_parts, one launch per part.
+//   * CHAIN (fewer GPUs than trajectories; the reference's own plan, hw5.cu:396-413, 438-530, 575-588): Q2 runs in
+//     chunks of NB_SOLVE_CHUNK steps with a device-to-device copy of its state before each chunk; a device whose
+//     missile arrives inside a chunk gets that copy as its fork point, so its Q3 trajectory starts at most one
+//     chunk before the arrival instead of at step 0 (a fork started before the arrival is bit-identical to a
+//     run from step 0).  The candidates are then tried in order of arrival step = order of cost, and the search
+//     stops at the first one that saves the planet (hw5.cu:491-492, 509-517): the others cost more.  Part 0 runs
+//     Q1 (in lock step with the chain when it is the only part), part 1 the chain; further parts stay idle.
+static const int NB_SOLVE_CHUNK = getenv("NB_SOLVE_CHUNK") ? atoi(getenv("NB_SOLVE_CHUNK")) : 8192;
+
+static bool solve_chain_plan(int n_parts, int n_traj, int math_flags) {
+    return n_parts < n_traj && !(math_flags & NB_SOLVE_ALL_DEVICES);
+}
+
 static int solve_jobs(const nb_system* sys, std::vector<int>& devs) {
     if (!sys || !sys->q || !sys->v || !sys->m || !sys->is_device || sys->n < 1) return NB_ERR_ARG;
     if (sys->n > NB_MAX_SMALL_N) return NB_ERR_UNSUPPORTED;
@@ -446,13 +480,135 @@ int nb_solve_trajectory_count(const nb_system* sys, int* count) {
     return NB_OK;
 }
 
+
+// CHAIN plan on one GPU (see above): slot 0 = Q1 (optional), last slot = Q2, then the Q3 candidates one after another
+static int solve_chain(const nb_system* sys, const std::vector<int>& devs, int gpu, bool with_q1, bool with_chain, int n_steps,
+                       int math, nb_events* evs, double* gpu_seconds, long long* pair_interactions) {
+    const bool verbose = getenv("NB_VERBOSE") != nullptr;
+    const int n = sys->n, dc = (int)devs.size();
+    const size_t sbytes = 3 * (size_t)n * sizeof(double);
+    int rc = nb::check_gpu(gpu);
+    if (rc) return rc;
+    DeviceBatch b;
+    const int S = (with_q1 ? 1 : 0) + (with_chain ? 1 : 0), sl = S - 1;  // sl = slot of the chain
+    rc = b.init(gpu, S, n, math);
+    if (!rc && with_q1) rc = b.set_system(0, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid, NB_KIND_Q1, -1, 0);
+    if (!rc && with_chain)
+        rc = b.set_system(sl, sys->q, sys->v, sys->m, sys->is_device, sys->planet, sys->asteroid, NB_KIND_Q2, -1, 0);
+    double* lag = nullptr;               // Q2's q, v at the start of the current chunk
+    std::vector<double*> snap(dc, nullptr);  // fork point of device k: q, v at the start of the chunk its missile arrived in
+    std::vector<int> snap_step(dc, -1);
+    auto cleanup = [&](int r) {
+        cudaSetDevice(gpu);
+        if (lag) cudaFree(lag);
+        for (double* p : snap)
+            if (p) cudaFree(p);
+        b.release();
+        return r;
+    };
+    if (rc) return cleanup(rc);
+    int n_launch = 0;
+    const auto t_run = std::chrono::steady_clock::now();
+    if (!with_chain) {
+        rc = b.run(n_steps, true);
+        if (!rc) evs[0] = b.h_ev[0];
+    } else {
+        if (cudaMalloc(&lag, 2 * sbytes) != cudaSuccess) return cleanup(NB_ERR_CUDA);
+        double* cq = b.q + (size_t)sl * 3 * n;
+        double* cv = b.v + (size_t)sl * 3 * n;
+        // ---- Q2 (and Q1 beside it), chunk by chunk while a missile is still under way
+        int cur = 0;
+        while (!rc && cur < n_steps && b.h_ev[sl].hit_step == -2) {
+            bool pending = false;
+            for (int k = 0; k < dc; k++) pending |= snap_step[k] < 0;
+            // chunks go on after the last arrival: Q1 (same launch) must not run ahead alone past Q2's hit, its remaining
+            // steps pair with the Q3 candidate's in one launch
+            const int next = cur + NB_SOLVE_CHUNK < n_steps ? cur + NB_SOLVE_CHUNK : n_steps;
+            if (pending) {
+                if (cudaMemcpyAsync(lag, cq, sbytes, cudaMemcpyDeviceToDevice, b.stream) != cudaSuccess ||
+                    cudaMemcpyAsync(lag + 3 * n, cv, sbytes, cudaMemcpyDeviceToDevice, b.stream) != cudaSuccess)
+                    return cleanup(NB_ERR_CUDA);
+            }
+            const double g_before = b.gpu_seconds;
+            rc = b.run(next, true);
+            n_launch++;
+            if (verbose) fprintf(stderr, "nbody_b200:   Q2 chunk %d -> %d: kernels %.4f s\n", cur, next, b.gpu_seconds - g_before);
+            for (int k = 0; k < dc && !rc; k++)
+                if (snap_step[k] < 0 && b.h_ev[sl].reach_step[k] != -2) {
+                    if (cudaMalloc(&snap[k], 2 * sbytes) != cudaSuccess ||
+                        cudaMemcpyAsync(snap[k], lag, 2 * sbytes, cudaMemcpyDeviceToDevice, b.stream) != cudaSuccess)
+                        return cleanup(NB_ERR_CUDA);
+                    snap_step[k] = cur;
+                }
+            cur = next;
+        }
+        if (rc) return cleanup(rc);
+        evs[1] = b.h_ev[sl];
+        for (int k = 0; k < dc; k++) {  // "not simulated" until tried
+            DeviceBatch::fresh_events(evs[2 + k]);
+        }
+        // ---- Q3: candidates by arrival step (= by cost, hw5.cu:575-585), first saviour wins (hw5.cu:491-492)
+        if (evs[1].hit_step != -2) {
+            std::vector<int> order;
+            for (int k = 0; k < dc; k++)
+                if (snap_step[k] >= 0) order.push_back(k);
+            std::stable_sort(order.begin(), order.end(),
+                             [&](int a, int c2) { return evs[1].reach_step[a] < evs[1].reach_step[c2]; });
+            for (int k : order) {
+                rc = b.set_system(sl, nullptr, nullptr, sys->m, sys->is_device, sys->planet, sys->asteroid, NB_KIND_Q3, devs[k],
+                                  snap_step[k]);
+                if (rc) return cleanup(rc);
+                if (cudaMemcpyAsync(cq, snap[k], sbytes, cudaMemcpyDeviceToDevice, b.stream) != cudaSuccess ||
+                    cudaMemcpyAsync(cv, snap[k] + 3 * n, sbytes, cudaMemcpyDeviceToDevice, b.stream) != cudaSuccess)
+                    return cleanup(NB_ERR_CUDA);
+                const double g_before = b.gpu_seconds;
+                rc = b.run(n_steps, true);  // Q1, if still under way, rides along in the same launch
+                n_launch++;
+                if (verbose)
+                    fprintf(stderr, "nbody_b200:   Q3 device %d from step %d: kernels %.4f s\n", devs[k], snap_step[k], b.gpu_seconds - g_before);
+                if (rc) return cleanup(rc);
+                evs[2 + k] = b.h_ev[sl];
+                if (b.h_ev[sl].hit_step == -2 && b.h_ev[sl].destroyed_step != -2) break;  // saved: the rest cost more
+            }
+        }
+        if (with_q1) {
+            if (b.cur_step[0] < n_steps) {
+                // nothing left to pair Q1 with: park the chain slot (a stopped trajectory never steps again)
+                rc = b.run(n_steps, true);
+                n_launch++;
+            }
+            if (!rc) evs[0] = b.h_ev[0];
+        }
+    }
+    if (verbose)
+        fprintf(stderr, "nbody_b200: gpu %d chain plan (%s%s): %d launches, run %.3f s (kernels %.3f s)\n", gpu,
+                with_q1 ? "Q1 " : "", with_chain ? "Q2 -> Q3 candidates" : "", n_launch,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count(), b.gpu_seconds);
+    if (gpu_seconds) *gpu_seconds = b.gpu_seconds;
+    if (pair_interactions) *pair_interactions = b.pairs;
+    return cleanup(rc);
+}
+
 int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n_steps, int math, nb_events* evs,
                      double* gpu_seconds, long long* pair_interactions) {
     std::vector<int> devs;
     int rc = solve_jobs(sys, devs);
     if (rc) return rc;
     if (!evs || n_parts < 1 || part < 0 || part >= n_parts || n_steps < 0) return NB_ERR_ARG;
+    const int math_flags = math;
+    math &= ~NB_SOLVE_ALL_DEVICES;
     if (math != NB_MATH_FAST && math != NB_MATH_STRICT) return NB_ERR_ARG;
+    for (int t = 0; t < 2 + (int)devs.size(); t++) {  // entries of other parts stay marked "not mine"
+        DeviceBatch::fresh_events(evs[t]);
+        evs[t].steps_done = -2;
+    }
+    if (gpu_seconds) *gpu_seconds = 0;
+    if (pair_interactions) *pair_interactions = 0;
+    if (solve_chain_plan(n_parts, 2 + (int)devs.size(), math_flags)) {
+        if (part > 1) return NB_OK;
+        return solve_chain(sys, devs, gpu, /*with_q1=*/part == 0, /*with_chain=*/n_parts == 1 || part == 1, n_steps, math, evs,
+                           gpu_seconds, pair_interactions);
+    }
     const bool verbose = getenv("NB_VERBOSE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(now() - t).count(); };
@@ -515,6 +671,7 @@ int nb_solve_combine(const nb_system* sys, const nb_events* evs, nb_answer* ans)
         double best = std::numeric_limits<double>::infinity();
         for (int k = 0; k < dc; k++) {
             const nb_events& e = evs[2 + k];
+            if (e.steps_done < 0) continue;  // not simulated (chain plan: a cheaper device already saved the planet)
             ans->q3_hit_step[k] = e.hit_step;
             ans->q3_cost[k] = e.cost;
             // hw5.cu:509-517: saved (no hit through n_steps) and cheapest; ties -> lowest device index
@@ -536,7 +693,8 @@ int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int
     if (!ans || n_gpus < 1 || n_steps < 0) return NB_ERR_ARG;
     auto t_begin = std::chrono::steady_clock::now();
     const int T = 2 + (int)devs.size();
-    const int G = n_gpus < T ? n_gpus : T;
+    int G = n_gpus < T ? n_gpus : T;
+    if (solve_chain_plan(G, T, math) && G > 2) G = 2;  // chain plan: Q1 on one GPU, Q2 -> Q3 on another
     std::vector<int> gl(G);
     for (int g = 0; g < G; g++) {
         gl[g] = gpus ? gpus[g] : g;
@@ -562,7 +720,8 @@ int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int
             nb::set_error_detail(details[g]);
             return rcs[g];
         }
-        for (int t = g; t < T; t += G) evs[t] = part_evs[g][t];
+        for (int t = 0; t < T; t++)
+            if (part_evs[g][t].steps_done != -2) evs[t] = part_evs[g][t];
     }
     rc = nb_solve_combine(sys, evs.data(), ans);
     if (rc) return rc;

@@ -46,6 +46,7 @@ int traj_js_for(int math, int n);
 int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs_dev, const double* fst_dev, int gpu,
                      void* workspace_dev, size_t workspace_bytes, cudaStream_t stream);
 size_t grid_traj_workspace_bytes(int n, int n_traj);
+const int* grid_traj_status(const void* workspace_dev, int n);  // sticky status word, read it once the stream is idle
 bool grid_traj_supported(int gpu, int n, int n_traj);
 
 }  // namespace nb

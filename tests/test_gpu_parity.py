@@ -90,7 +90,7 @@ def test_edge_sizes_small_path(nb, oracle, n):
 def test_solve_matches_golden(nb, case, kats):
     s = nb.read_input(case_path(case))
     g = golden_lines(case)
-    ans = nb.solve(s, gpus=[0])
+    ans = nb.solve(s, gpus=[0], all_devices=True)  # INDEPENDENT plan: every device's trajectory from step 0
     assert ans.hit_time_step == g["hit_time_step"]            # bit-exact
     assert ans.gravity_device_id == g["gravity_device_id"]    # bit-exact
     assert ans.missile_cost == g["missile_cost"]              # bit-exact
@@ -102,6 +102,29 @@ def test_solve_matches_golden(nb, case, kats):
             assert ans.device_index[j] == d["index"]
             assert ans.reach_step[j] == d["reach_step"]
             assert ans.q3_hit_step[j] == d["q3_hit_step"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_solve_chain_plan_matches_golden(nb, case, kats):
+    """Default plan on one GPU (fewer GPUs than trajectories): query 3 forked from query 2 at most one chunk before the
+    missile arrives, candidates in order of cost, search stopped at the first saviour (hw5.cu:438-530, 575-588).  Same
+    answers as the goldens; the devices it did simulate agree with the oracle's KATs, the others read -3."""
+    s = nb.read_input(case_path(case))
+    g = golden_lines(case)
+    ans = nb.solve(s, gpus=[0])
+    assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (g["hit_time_step"], g["gravity_device_id"], g["missile_cost"])
+    assert abs(ans.min_dist - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+    if case in kats:
+        k = kats[case]
+        assert ans.argmin_step == k["argmin_step"]
+        simulated = 0
+        for j, d in enumerate(k["devices"]):
+            assert ans.reach_step[j] == d["reach_step"]
+            if ans.q3_hit_step[j] != -3:
+                simulated += 1
+                assert ans.q3_hit_step[j] == d["q3_hit_step"]
+        saviours = [d for d in k["devices"] if d["q3_hit_step"] == -2]
+        assert simulated == (1 if saviours else len(k["devices"]))  # the cheapest saviour is the first candidate tried
 
 
 def test_solve_output_file_is_byte_identical_for_small_goldens(nb, tmp_path):
@@ -208,7 +231,7 @@ def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
         "out = {}\n"
         "for case in ('b100', 'b200', 'b90'):\n"
         "    s = nb.read_input(%r + '/' + case + '.in')\n"
-        "    a = nb.solve(s, gpus=[0])\n"
+        "    a = nb.solve(s, gpus=[0], all_devices=True)\n"
         "    out[case] = dict(text=nb.format_output(a.min_dist, a.hit_time_step, a.gravity_device_id, a.missile_cost),\n"
         "                     argmin=a.argmin_step, reach=list(a.reach_step[:a.n_devices]), q3=list(a.q3_hit_step[:a.n_devices]))\n"
         "print(json.dumps(out))\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),

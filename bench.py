@@ -257,7 +257,7 @@ def run_ours(args):
         ok = tl[1] == gl[1] and tl[2] == gl[2] and abs(float(tl[0]) - float(gl[0])) <= 1e-6 * float(gl[0])
         b1024 = {"solve_wall_s": wall, "gpu_s": gsecs, "pairs_per_s_gpu": pairs / gsecs if gsecs else None,
                  "trajectories": ans.n_trajectories, "matches_golden": bool(ok), "line1_byte_identical": tl[0] == gl[0],
-                 "note": "in-process solve (contexts already created); Q1, Q2 and one Q3 trajectory per device over the N ranks"}
+                 "note": "in-process solve (contexts already created); as many GPUs as trajectories: Q1, Q2 and one Q3 trajectory per device from step 0, one per rank; fewer: Q1 on rank 0, Q2 -> Q3 candidates forked from Q2 on rank 1 (chain plan, nb_host.cu)"}
 
     # ---- CPU baseline: the unmodified reference program on this box's host cores --------------------
     cpu = None

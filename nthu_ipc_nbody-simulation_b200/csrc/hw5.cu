@@ -1,4 +1,6 @@
 // hw5 <input> <output> — same CLI and files as the reference (hw5.cu:532-535, nbody.cc:91-94).
+#include <unistd.h>
+
 #include <cstdio>
 #include <stdexcept>
 
@@ -13,5 +15,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "hw5: %s: %s\n", nb_strerror(rc), nb_last_error_detail());
         return 1;
     }
-    return 0;
+    // The output file is written and closed.  Leave without tearing the CUDA contexts down (0.3-0.5 s per process on the
+    // B200 boxes): the operating system reclaims everything.
+    fflush(nullptr);
+    _exit(0);
 }

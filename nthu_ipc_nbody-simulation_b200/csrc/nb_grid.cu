@@ -689,11 +689,12 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     long long* prof = (long long*)((char*)ws + w.gbuf_bytes + 64);
     static const bool profile = env_int("NB_GRID_PROFILE", 0) != 0;
     // copy delay after the trigger (SM clocks): one system per launch waits for every copy, so it wants the shortest
-    // delay that keeps the polling rare (measured: 3.25 us/step at 600 clk, 3.17 at 700-800, 3.21 at 900, 3.31 at 1100); with two systems in lock step the copy of one hides
+    // delay that keeps the polling rare (measured on one box: 3.25 us/step at 600 clk, 3.17 at 700-800, 3.21 at 900, 3.31 at
+    // 1100; on another box 750 gave 3.9 and 900 gave 3.2, so 900 it is); with two systems in lock step the copy of one hides
     // behind the pair loop of the other and a longer delay (fewer stale records, fewer polls) wins (measured: b1024
     // four-trajectory solve on one GPU 2.33 s at 900, 2.00 s at 2600)
-    static const int delay_clk_env = env_int("NB_GRID_DELAY", T == 1 ? 750 : 2600);
-    static const int delay_single_env = env_int("NB_GRID_DELAY", 750);
+    static const int delay_clk_env = env_int("NB_GRID_DELAY", T == 1 ? 900 : 2600);
+    static const int delay_single_env = env_int("NB_GRID_DELAY", 900);
     auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true> : grid_traj_kernel<MATH, T, NJ, false>;
     NB_CUDA(cudaMemsetAsync(ws, 0, w.gbuf_bytes, stream));  // tag 0 = no step
     if (profile) NB_CUDA(cudaMemsetAsync(prof, 0, NPROF * sizeof(long long), stream));

@@ -203,9 +203,17 @@ int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
     lap("read input");
     int n_traj = 2;
     for (int i = 0; i < n; i++) n_traj += dev[i] ? 1 : 0;
+    // How many GPUs: the driver initialises every VISIBLE device (0.6-0.9 s each on the B200 boxes, 2.0-2.6 s for four) and
+    // a context costs another 0.6-1.6 s per used GPU, while the kernels of b1024 take 1.11 s on one GPU, 0.73 s on two and
+    // 0.65 s on four (chain / independent plan, nb_host.cu).  Measured end to end on a 2-GPU box: one GPU 2.5-3.2 s, two
+    // GPUs 3.1-3.5 s - the second context costs more than its kernels save, so the CLI uses ONE GPU unless told otherwise
+    // (NB_HW5_GPUS, or the n_gpus argument of nb_hw5_main).
+    if (n_gpus <= 0) n_gpus = getenv("NB_HW5_GPUS") ? atoi(getenv("NB_HW5_GPUS")) : 1;
+    if (n_gpus < 1) n_gpus = 1;
+    if (n_gpus > n_traj) n_gpus = n_traj;
     if (!getenv("CUDA_VISIBLE_DEVICES")) {
         const int present = count_gpus_procfs();
-        int want = n_gpus > 0 ? n_gpus : n_traj;
+        const int want = n_gpus;
         if (present > 0 && want < present) {
             std::string list;
             for (int g = 0; g < want; g++) list += (g ? "," : "") + std::to_string(g);
@@ -213,9 +221,11 @@ int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
             if (verbose) fprintf(stderr, "nbody_b200: %d GPUs present, using CUDA_VISIBLE_DEVICES=%s\n", present, list.c_str());
         }
     }
-    if (n_gpus <= 0) {
-        rc = nb_device_count(&n_gpus);
+    {
+        int have = 0;
+        rc = nb_device_count(&have);
         if (rc) return rc;
+        if (n_gpus > have) n_gpus = have;
     }
     lap("driver initialisation");
     nb_system sys{n, planet, asteroid, q.data(), v.data(), m.data(), dev.data()};

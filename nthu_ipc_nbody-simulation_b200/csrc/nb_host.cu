@@ -518,7 +518,9 @@ static int solve_chain(const nb_system* sys, const std::vector<int>& devs, int g
         double* cv = b.v + (size_t)sl * 3 * n;
         // ---- Q2 (and Q1 beside it), chunk by chunk while a missile is still under way
         int cur = 0;
-        while (!rc && cur < n_steps && b.h_ev[sl].hit_step == -2) {
+        bool first = true;  // n_steps == 0 still observes step 0
+        while (!rc && (first || (cur < n_steps && b.h_ev[sl].hit_step == -2))) {
+            first = false;
             bool pending = false;
             for (int k = 0; k < dc; k++) pending |= snap_step[k] < 0;
             // chunks go on after the last arrival: Q1 (same launch) must not run ahead alone past Q2's hit, its remaining

@@ -162,6 +162,30 @@ def test_no_hit_defaults(nb, oracle):
 
 
 # ---- trajectories / events -------------------------------------------------------------------------
+def test_solve_plans_on_edge_cases(nb, oracle):
+    """Both scheduler plans against the oracle where the goldens have no case: zero steps, one step, no devices at all,
+    a collision in the initial state (nbody.cc:131-137 tests step 0 too), fewer steps than any missile needs."""
+    base = nb.read_input(case_path("b20"))
+    nodev = base.copy()
+    nodev.is_device[:] = 0
+    crash = base.copy()
+    for k in range(3):
+        crash.q[k * crash.n + crash.asteroid] = crash.q[k * crash.n + crash.planet] + 1.0e6
+    big = nb.read_input(case_path("b200"))  # n >= 128: the whole-GPU kernel
+    bigcrash = big.copy()
+    for k in range(3):
+        bigcrash.q[k * big.n + big.asteroid] = bigcrash.q[k * big.n + big.planet] + 1.0e6
+    for name, s, n_steps in (("zero steps", base, 0), ("one step", base, 1), ("no devices", nodev, 3000),
+                             ("hit at step 0", crash, 50), ("short", base, 2500), ("zero steps, b200", big, 0),
+                             ("hit at step 0, b200", bigcrash, 40), ("short, b200", big, 300)):
+        ref = oracle.solve(oracle.MODE_STRICT, s, n_steps=n_steps)
+        for all_devices in (False, True):
+            ans = nb.solve(s, gpus=[0], n_steps=n_steps, all_devices=all_devices)
+            assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (
+                ref.hit_time_step, ref.gravity_device_id, ref.missile_cost), (name, all_devices)
+            assert abs(ans.min_dist - ref.min_dist) <= MIN_DIST_RTOL * ref.min_dist, (name, all_devices)
+
+
 def test_trajectory_events_match_oracle(nb, oracle):
     s = nb.read_input(case_path("b30"))
     for kind, okind, dd in ((nb.KIND_Q1, oracle.KIND_Q1, -1), (nb.KIND_Q2, oracle.KIND_Q2, -1),

@@ -52,8 +52,6 @@
 // Tried and measured worse: validating inside the pair loop (a vote per record batch serialises the loop),
 // optimistic pair loop + redo on a stale record (a redone block is late, all others find it stale: cascade),
 // per-block adaptive delays (creep up together), rotating the tag slot for conflict-free validation loads.
-#include <cooperative_groups.h>
-
 #include <cstdint>
 #include <cstdio>
 #include <chrono>

@@ -108,6 +108,8 @@ struct DeviceBatch {
     size_t grid_ws_bytes = 0;
     std::vector<TrajDesc> h_descs;
     std::vector<nb_events> h_ev;
+    nb_events* pin_ev = nullptr;  // pinned staging for the events + the grid kernel's status word: the D2H copies after a
+    int* pin_status = nullptr;    // launch are then truly asynchronous and run() does the waiting itself (busy-wait)
     std::vector<int> cur_step;
     double gpu_seconds = 0.0;
     long long pairs = 0;
@@ -125,6 +127,8 @@ struct DeviceBatch {
         NB_CUDA(cudaMalloc(&devidx, (size_t)S * NB_MAX_DEVICES * sizeof(int)));
         NB_CUDA(cudaMalloc(&ev, (size_t)S * sizeof(nb_events)));
         NB_CUDA(cudaMalloc(&descs, (size_t)S * sizeof(TrajDesc)));
+        NB_CUDA(cudaHostAlloc(&pin_ev, (size_t)S * sizeof(nb_events), cudaHostAllocDefault));
+        NB_CUDA(cudaHostAlloc(&pin_status, 64, cudaHostAllocDefault));
         h_descs.assign(S, TrajDesc{});
         h_ev.assign(S, nb_events{});
         cur_step.assign(S, 0);
@@ -135,6 +139,9 @@ struct DeviceBatch {
         cudaSetDevice(gpu);
         cudaFree(q), cudaFree(v), cudaFree(m), cudaFree(isdev), cudaFree(devidx), cudaFree(ev), cudaFree(descs);
         if (grid_ws) cudaFree(grid_ws);
+        if (pin_ev) cudaFreeHost(pin_ev);
+        if (pin_status) cudaFreeHost(pin_status);
+        pin_ev = nullptr, pin_status = nullptr;
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
         if (stream) cudaStreamDestroy(stream);
@@ -221,9 +228,9 @@ struct DeviceBatch {
             static const bool verbose = getenv("NB_VERBOSE") != nullptr;
             if (verbose && hms > 2.0) fprintf(stderr, "nbody_b200:   host spent %.1f ms between the two event records\n", hms);
         }
-        NB_CUDA(cudaMemcpyAsync(h_ev.data(), ev, S * sizeof(nb_events), cudaMemcpyDeviceToHost, stream));
-        int grid_status = 0;
-        if (grid) NB_CUDA(cudaMemcpyAsync(&grid_status, grid_traj_status(grid_ws, n), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        NB_CUDA(cudaMemcpyAsync(pin_ev, ev, S * sizeof(nb_events), cudaMemcpyDeviceToHost, stream));
+        *pin_status = 0;
+        if (grid) NB_CUDA(cudaMemcpyAsync(pin_status, grid_traj_status(grid_ws, n), sizeof(int), cudaMemcpyDeviceToHost, stream));
         // Busy-wait instead of cudaStreamSynchronize: the blocking wait costs tens of milliseconds of wake-up latency now
         // and then (measured on the B200 boxes), and the chain plan of nb_solve comes through here every few thousand steps.
         for (;;) {
@@ -231,7 +238,8 @@ struct DeviceBatch {
             if (qe == cudaSuccess) break;
             if (qe != cudaErrorNotReady) return cuda_fail(qe, "cudaStreamQuery", __FILE__, __LINE__);
         }
-        if (grid_status != 0) {
+        memcpy(h_ev.data(), pin_ev, S * sizeof(nb_events));
+        if (*pin_status != 0) {
             set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
             return NB_ERR_CUDA;
         }

@@ -497,7 +497,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 int flags = 0;
                 if (!last) {
                     // (0) validate: every record of the stage must carry this step's tag (thread tid checks records
-                    //     tid + 256k; the rotating tag slot makes each warp's LDS.64 conflict-free).  A stale record was copied
+                    //     tid + 256k; the tags of 32 consecutive records share 8 banks, so this pass is shared-memory bound: ~256 clk at
+                    //     n = 1024).  A stale record was copied
                     //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
                     //     memory and patch shared memory, each stale record by exactly one thread of the block.
                     bool patched = false;

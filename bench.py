@@ -91,49 +91,98 @@ def run_reference_arm(args):
 
 
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: NVML from a thread every ~2 ms
+    (a timed region can be as short as 10 ms at 8 GPUs), `nvidia-smi -lms 20` as the fallback."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    MASKS = [0x8, 0x40, 0x20, 0x4]  # nvmlClocksThrottleReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, uuid):
-        self.proc = None
+        self.proc, self.nvml, self.rows, self.lines, self.source = None, None, [], [], None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml, 2 ms"
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", uuid, "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 20"
         except Exception:
             pass
-        self.lines = []
         if self.proc:
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                ts = time.perf_counter()
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((ts, sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, pw, reasons = [], None, [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, ln in self.lines:
-            if ts < t0 or ts > t1 + 0.1:
-                continue
-            f = [x.strip() for x in ln.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-                pw.append(float(f[2]))
-                for nme, val in zip(names, f[3:7]):
-                    if val.lower().startswith("active"):
+        if self.nvml:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            mx = self.mx
+            for ts, s_, p_, rs in self.rows:
+                if ts < t0 or ts > t1:
+                    continue
+                sm.append(s_)
+                pw.append(p_)
+                for nme, msk in zip(self.NAMES, self.MASKS):
+                    if rs & msk:
                         reasons.add(nme)
-            except Exception:
-                continue
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            for ts, ln in self.lines:
+                if ts < t0 or ts > t1 + 0.1:
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    mx = float(f[1])
+                    pw.append(float(f[2]))
+                    for nme, val in zip(self.NAMES, f[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nme)
+                except Exception:
+                    continue
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML, no nvidia-smi"]}
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": self.source}
 
 
 def run_ours(args):
@@ -343,7 +392,11 @@ def run_ensemble(args):
         return float(t[0]), float(t[1]), ev, q
 
     once(max(args.warmup, 1))
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid) if rank == 0 else None
+    ts0 = time.perf_counter()
     secs, wall, ev, q = once(args.steps)
+    clocks = sampler.stop(ts0, time.perf_counter()) if sampler else None
     # member 0 of rank 0 is the golden system itself: its state must equal a plain trajectory's
     ok = True
     if rank == 0:
@@ -362,7 +415,10 @@ def run_ensemble(args):
             "frac_of_fp64_peak": pairs / secs * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
             "e2e": {"value": pairs / wall, "unit": UNIT, "h2d_bytes_per_step": int(S * n * 57 / args.steps),
                     "d2h_bytes_per_step": int(S * n * 48 / args.steps), "note": "states uploaded once per launch, not per step"},
-            "member0_equals_single_trajectory": ok, "gpu_launches": 2}), flush=True)
+            "roofline": {"bound": "fp64", "achieved": pairs / secs * PAIR_FLOPS / 1e12 / world, "peak": FP64_PEAK_NOMINAL_TFLOPS,
+                         "unit": "TFLOP/s", "frac": pairs / secs * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
+                         "traffic": None, "kernel": "traj_kernel", "note": "per GPU; the whole launch is this kernel"},
+            "clocks": clocks, "member0_equals_single_trajectory": ok, "gpu_launches": 2}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

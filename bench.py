@@ -90,6 +90,23 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def init_nccl(dist, torch, dev):
+    """init_process_group + the first collective with file descriptor 1 pointed at stderr: NCCL prints its version
+    banner (NCCL_DEBUG=VERSION on these boxes) to stdout when the communicator is created, and stdout must carry the
+    one JSON line only."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ClockSampler:
     """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: NVML from a thread every ~2 ms
     (a timed region can be as short as 10 ms at 8 GPUs), `nvidia-smi -lms 20` as the fallback."""
@@ -200,9 +217,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner (and any debug output) to stdout by default
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dist, torch, dev)
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
 
@@ -368,7 +383,7 @@ def run_ensemble(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dist, torch, dev)
     S_total = args.systems
     base = nb.read_input(os.path.join(CASES, "b1024.in"))
     mine = list(range(rank, S_total, world))

@@ -216,6 +216,46 @@ int nb_ipc_export(void* dev_ptr, unsigned char* handle64);
 int nb_ipc_open(const unsigned char* handle64, void** dev_ptr);
 int nb_ipc_close(void* dev_ptr);
 
+/* ---- large systems, symmetric stepper (FAST math) ---------------------------------------------------
+ * The same step as nb_large_step_p2p (run_step, nbody.cc:51-89; replaces hw5.cu:159-215 + 231-239) with every
+ * UNORDERED pair evaluated once: both a_i and a_j are accumulated, 10 FP64 instructions per ordered pair.
+ * Rank r of `world` holds shard [r*n/world, (r+1)*n/world) and evaluates the block pairs (r, r) .. (r, r + world/2);
+ * the partial accelerations of a body are stored straight into the memory of the rank that owns it (PJ, a
+ * peer-mapped buffer of nb_sym_pj_bytes() bytes per rank) and its integrate kernel sums them in a fixed order,
+ * integrates and stores the new pos4 record into EVERY rank's next-step buffer.  Arrival is signalled through
+ * per-rank counter blocks (nb_sym_counter_bytes() bytes, zeroed, peer-mapped) with system-scope release/acquire;
+ * the kernels wait on them in-kernel, so a step is two launches and no host synchronisation or NCCL call.
+ * world == 1: the peer arrays have one entry (own buffers), counters / status may be NULL.
+ * Steps must be consecutive (the counters count them).  pos4 layout as above: [n][4] doubles. */
+typedef struct nb_sym nb_sym;
+int nb_sym_create(int n, int world, int rank, nb_sym** out); /* on the current CUDA device */
+int nb_sym_destroy(nb_sym* h);
+long long nb_sym_pj_bytes(const nb_sym* h);
+int nb_sym_counter_bytes(void);
+int nb_sym_blocks(const nb_sym* h);
+long long nb_sym_remote_partial_bytes(const nb_sym* h); /* bytes of partial rows this rank stores into peers per step */
+/* ordered pair interactions one step of this rank covers (= 2 x symmetric + one-sided) */
+long long nb_sym_pairs(const nb_sym* h, long long* sym_pairs, long long* onesided_pairs);
+/* stream-ordered wait until every rank's rows of the last step are in this rank's buffer (before the host reads it) */
+int nb_sym_wait_positions(nb_sym* h, const unsigned long long* my_counters, int* status_dev, void* stream);
+int nb_sym_step(nb_sym* h, int step, const double* pos4_cur_dev, double* const* peer_pos4_next,
+                double* const* peer_pj, unsigned long long* const* peer_counters, int* status_dev,
+                double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* stream);
+/* One step in two calls: phases = 1 launches the acceleration kernel, 2 the integrate kernel, 3 both (= nb_sym_step).
+ * With every rank's phase 1 enqueued before any rank's phase 2, several ranks can share ONE GPU and one stream (each
+ * in-kernel wait is then already satisfied when it is reached): the multi-rank path is testable on a 1-GPU box. */
+int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur_dev, double* const* peer_pos4_next,
+                      double* const* peer_pj, unsigned long long* const* peer_counters, int* status_dev,
+                      double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* stream);
+/* The static schedule of one rank (host only, no GPU needed): segments of eight ints
+ * {row_body0, row_count, j0, j1, flags, pi_slot, pj_row, src_rank} (flags: 1 = one-sided, 2 = load row, 4 = flush row),
+ * block b owns segments [block_seg_begin[b], block_seg_begin[b+1]); pj_ptr / pj_list = per local row the PJ rows
+ * that hold contributions to its bodies.  Any output pointer may be NULL. */
+int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, int* segs_out, int* n_segs,
+                         int* block_seg_begin, int* pj_ptr, int* pj_list, int max_pj, long long* sym_pairs,
+                         long long* onesided_pairs);
+int nb_sym_rows(int n, int world); /* rows (superblocks of 1024 bodies) per rank */
+
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */
 int nb_fp64_peak(int gpu, double* tflops, double* seconds);

@@ -72,6 +72,8 @@ ABI_SYMBOLS = [
     "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_write_input", "nb_generate_system", "nb_hw5_main",
     "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_large_step_p2p", "nb_large_blocks_per_step", "nb_large_p2p_counter_bytes", "nb_large_wait_p2p",
     "nb_dev_alloc", "nb_dev_free", "nb_dev_copy", "nb_ipc_export", "nb_ipc_open", "nb_ipc_close", "nb_fp64_peak", "nb_fp64_peak_variant",
+    "nb_sym_create", "nb_sym_destroy", "nb_sym_pj_bytes", "nb_sym_counter_bytes", "nb_sym_blocks", "nb_sym_remote_partial_bytes",
+    "nb_sym_pairs", "nb_sym_wait_positions", "nb_sym_step", "nb_sym_step_phase", "nb_sym_plan_describe", "nb_sym_rows",
 ]
 
 _lib_handle = None
@@ -134,6 +136,23 @@ def lib():
     L.nb_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
     L.nb_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.nb_ipc_close.argtypes = [C.c_void_p]
+    L.nb_sym_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.nb_sym_destroy.argtypes = [C.c_void_p]
+    L.nb_sym_pj_bytes.restype = C.c_longlong
+    L.nb_sym_pj_bytes.argtypes = [C.c_void_p]
+    L.nb_sym_blocks.argtypes = [C.c_void_p]
+    L.nb_sym_remote_partial_bytes.restype = C.c_longlong
+    L.nb_sym_remote_partial_bytes.argtypes = [C.c_void_p]
+    L.nb_sym_pairs.restype = C.c_longlong
+    L.nb_sym_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.nb_sym_wait_positions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_sym_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                              C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_sym_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_sym_plan_describe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip, C.c_int,
+                                       C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.nb_sym_rows.argtypes = [C.c_int, C.c_int]
     L.nb_fp64_peak.argtypes = [C.c_int, _dp, _dp]
     L.nb_fp64_peak_variant.argtypes = [C.c_int, C.c_int, _dp]
     _lib_handle = L
@@ -365,6 +384,24 @@ def solve_distributed(system, rank, world, gpu, n_steps=N_STEPS, math=MATH_FAST,
     return solve_combine(system, evs), secs, pairs
 
 
+def sym_plan(n, world, rank, blocks):
+    """The static schedule of the symmetric large-N stepper for one rank (host only, csrc/nb_sym.cu build_plan):
+    returns (segs[k, 8] = {row_body0, row_count, j0, j1, flags, pi_slot, pj_row, src_rank}, block_seg_begin[blocks+1],
+    pj_ptr[rows+1], pj_list, symmetric unordered pairs, one-sided ordered pairs)."""
+    L = lib()
+    ns, sp, op = C.c_int(), C.c_longlong(), C.c_longlong()
+    _check(L.nb_sym_plan_describe(n, world, rank, blocks, 0, None, C.byref(ns), None, None, None, 0, C.byref(sp), C.byref(op)))
+    segs = np.zeros((max(ns.value, 1), 8), dtype=np.int32)
+    bsb = np.zeros(blocks + 1, dtype=np.int32)
+    rows = L.nb_sym_rows(n, world)
+    pj_ptr = np.zeros(rows + 1, dtype=np.int32)
+    max_pj = rows * rows * world + 1
+    pj_list = np.zeros(max_pj, dtype=np.int32)
+    _check(L.nb_sym_plan_describe(n, world, rank, blocks, len(segs), _i(segs), C.byref(ns), _i(bsb), _i(pj_ptr), _i(pj_list),
+                                  max_pj, C.byref(sp), C.byref(op)))
+    return segs[: ns.value], bsb, pj_ptr, pj_list[: pj_ptr[-1]], sp.value, op.value
+
+
 def profile_enable(on=True):
     _check(lib().nb_profile_enable(1 if on else 0))
 
@@ -393,4 +430,4 @@ def fp64_peak(gpu=0, variant=0):
     return t.value
 
 
-from .sharded import P2PShardedSystem, ShardedSystem, partition, synthetic_system  # noqa: E402,F401
+from .sharded import P2PShardedSystem, ShardedSystem, SymLocalWorld, SymShardedSystem, partition, synthetic_system  # noqa: E402,F401

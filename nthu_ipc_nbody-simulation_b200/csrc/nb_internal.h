@@ -30,6 +30,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 void count_launch(int n = 1);
+// nb_profile_enable / nb_profile_read (nb_large.cu): event pairs around the acceleration kernel, calling thread only
+bool profile_on();
+void profile_push(cudaEvent_t e0, cudaEvent_t e1);
 
 // per-GPU |sin(step*dt/6000)| table (host glibc sin: nbody.cc:14-16 with t = step*dt, nbody.cc:63),
 // entries 0..len-1, built lazily and grown on demand.  Returns a device pointer valid for the

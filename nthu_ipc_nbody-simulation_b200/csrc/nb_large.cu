@@ -320,6 +320,10 @@ int launch_accel(int ipt, dim3 grid, cudaStream_t st, const double4* pos4, int n
 }
 
 }  // namespace
+
+bool profile_on() { return g_prof.on; }
+void profile_push(cudaEvent_t e0, cudaEvent_t e1) { g_prof.evs.emplace_back(e0, e1); }
+
 }  // namespace nb
 
 using namespace nb;
@@ -504,9 +508,16 @@ int nb_profile_read(double* accel_ms, long long* accel_launches) {
     return NB_OK;
 }
 
+int nb_sym_run_steps_host(int gpu, int n, double* q, double* v, const double* m, const unsigned char* is_device,
+                          int step_begin, int step_end);  // nb_sym.cu
+
 // host-buffer convenience used by nb_run_steps for n > NB_MAX_SMALL_N (single GPU, all bodies local)
 int nb_large_run_steps_host(int gpu, int math, int n, double* q, double* v, const double* m,
                             const unsigned char* is_device, int step_begin, int step_end) {
+    // FAST math takes the symmetric stepper (nb_sym.cu: every unordered pair once); NB_LARGE_SYM=0 keeps the
+    // row kernel below, which STRICT always uses (ascending-j sum of the reference)
+    static const bool use_sym = !(getenv("NB_LARGE_SYM") && atoi(getenv("NB_LARGE_SYM")) == 0);
+    if (math == NB_MATH_FAST && use_sym) return nb_sym_run_steps_host(gpu, n, q, v, m, is_device, step_begin, step_end);
     NB_CUDA(cudaSetDevice(gpu));
     cudaStream_t st;
     NB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));

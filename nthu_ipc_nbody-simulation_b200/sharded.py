@@ -220,6 +220,191 @@ class P2PShardedSystem:
         self.opened, self.own = [], []
 
 
+class SymShardedSystem:
+    """Body-sharded driver on the SYMMETRIC stepper (csrc/nb_sym.cu, FAST math): every unordered pair is evaluated
+    once (10 FP64 instructions per ordered pair), rank p takes the block pairs (p, p) .. (p, p + P/2); the partial
+    accelerations of a body are stored by the acceleration kernel straight into the memory of the rank that owns it
+    (peer-mapped PJ buffers over NVLink), its integrate kernel sums them in a fixed order and stores the new pos4
+    row into every rank's buffer.  Arrival counters + in-kernel waits: two launches per step, no NCCL call and no
+    host synchronisation on the data path (torch.distributed only carries the 64-byte IPC handles once)."""
+
+    def __init__(self, system, rank=0, world=1, device=None, math=0, group=None, step0=0, _local_world=None):
+        import ctypes as C
+
+        import torch
+
+        from . import MATH_FAST, _check, lib
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("SymShardedSystem needs a CUDA device (no CPU fallback)")
+        if math != MATH_FAST:
+            raise ValueError("the symmetric stepper is FAST math only (STRICT keeps the reference's ascending-j sum)")
+        self.torch, self.C, self.L = torch, C, lib()
+        L = self.L
+        self.n, self.rank, self.world, self.group, self.math = system.n, rank, world, group, math
+        self.i_begin, self.i_count = partition(system.n, world, rank)
+        self.step = self.step0 = step0
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        n, ib, ic = self.n, self.i_begin, self.i_count
+        self.h = C.c_void_p()
+        _check(L.nb_sym_create(n, world, rank, C.byref(self.h)))
+        self.m0 = torch.from_numpy(system.m.copy()).to(self.device)
+        self.isdev = torch.from_numpy(system.is_device.copy()).to(self.device)
+        self.vel = torch.from_numpy(system.v.reshape(3, n)[:, ib:ib + ic].copy()).to(self.device).contiguous()
+        self.ctr_bytes = int(L.nb_sym_counter_bytes())
+        self.pj_bytes = int(L.nb_sym_pj_bytes(self.h))
+        # own peer-visible buffers: pos4[2], PJ (partial accelerations of my bodies), {counters, status}
+        self.own = []
+        for nbytes in (32 * n, 32 * n, self.pj_bytes, self.ctr_bytes + 64):
+            ptr = C.c_void_p()
+            _check(L.nb_dev_alloc(nbytes, C.byref(ptr)))
+            self.own.append(ptr.value)
+        self.opened = []
+        self.cur = 0
+        qd = torch.from_numpy(system.q.copy()).to(self.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _check(L.nb_large_pack(math, n, C.c_void_p(qd.data_ptr()), C.c_void_p(self.m0.data_ptr()),
+                               C.c_void_p(self.isdev.data_ptr()), self.step + 1, C.c_void_p(self.own[0]), C.c_void_p(st)))
+        torch.cuda.current_stream().synchronize()
+        if _local_world is not None:
+            return  # SymLocalWorld connects the ranks (all on this GPU)
+        peers = [list(self.own)]
+        if world > 1:
+            import torch.distributed as dist
+
+            handles = []
+            for ptr in self.own:
+                h = C.create_string_buffer(64)
+                _check(L.nb_ipc_export(C.c_void_p(ptr), h))
+                handles.append(h.raw)
+            allh = [None] * world
+            dist.all_gather_object(allh, handles, group=group)
+            peers = []
+            for r in range(world):
+                if r == rank:
+                    peers.append(list(self.own))
+                    continue
+                ptrs = []
+                for raw in allh[r]:
+                    ptr = C.c_void_p()
+                    _check(L.nb_ipc_open(raw, C.byref(ptr)))
+                    ptrs.append(ptr.value)
+                    self.opened.append(ptr.value)
+                peers.append(ptrs)
+        self._connect(peers)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=group)  # every peer has mapped every buffer before the first remote store
+
+    def _connect(self, peers):
+        vp = self.C.c_void_p * self.world
+        self.peer_pos = [vp(*[peers[r][b] for r in range(self.world)]) for b in range(2)]
+        self.peer_pj = vp(*[peers[r][2] for r in range(self.world)])
+        self.peer_ctr = vp(*[peers[r][3] for r in range(self.world)])
+
+    def step_phase(self, phases):
+        """phases: 1 = acceleration kernel of the next step, 2 = its integrate kernel (advances the step), 3 = both."""
+        from . import _check
+
+        C, L = self.C, self.L
+        st = self.torch.cuda.current_stream().cuda_stream
+        step = self.step + 1
+        _check(L.nb_sym_step_phase(self.h, step, phases, C.c_void_p(self.own[self.cur]), self.peer_pos[self.cur ^ 1],
+                                   self.peer_pj, self.peer_ctr, C.c_void_p(self.own[3] + self.ctr_bytes),
+                                   C.c_void_p(self.vel.data_ptr()), C.c_void_p(self.m0.data_ptr()),
+                                   C.c_void_p(self.isdev.data_ptr()), C.c_void_p(st)))
+        if phases & 2:
+            self.step = step
+            self.cur ^= 1
+
+    def bytes_exchanged_per_step(self):
+        """Bytes this rank stores into peers' memory per step: pos4 rows to everybody + partial accelerations."""
+        if self.world == 1:
+            return 0
+        return 32 * self.i_count * (self.world - 1) + int(self.L.nb_sym_remote_partial_bytes(self.h))
+
+    def advance(self, steps=1):
+        for _ in range(steps):
+            self.step_phase(3)
+
+    def positions(self):
+        """Planar q[3n] of all bodies (host numpy); waits for the last step's rows of every rank."""
+        from . import _check
+
+        C, torch = self.C, self.torch
+        st = torch.cuda.current_stream().cuda_stream
+        if self.step > self.step0 and self.world > 1:
+            _check(self.L.nb_sym_wait_positions(self.h, C.c_void_p(self.own[3]), C.c_void_p(self.own[3] + self.ctr_bytes),
+                                                C.c_void_p(st)))
+        p = np.empty((self.n, 4))
+        _check(self.L.nb_dev_copy(p.ctypes.data_as(C.c_void_p), C.c_void_p(self.own[self.cur]), p.nbytes, 1, C.c_void_p(st)))
+        status = np.zeros(1, dtype=np.int32)
+        _check(self.L.nb_dev_copy(status.ctypes.data_as(C.c_void_p), C.c_void_p(self.own[3] + self.ctr_bytes), 4, 1, C.c_void_p(st)))
+        if status[0] != 0:
+            raise RuntimeError("symmetric P2P exchange: a peer's rows or partials did not arrive (wait timed out, status %d)" % status[0])
+        return np.ascontiguousarray(p[:, :3].T).reshape(-1)
+
+    def velocities(self):
+        torch = self.torch
+        if self.world == 1:
+            return self.vel.detach().to("cpu").numpy().reshape(-1).copy()
+        import torch.distributed as dist
+
+        parts = [torch.empty_like(self.vel) for _ in range(self.world)]
+        dist.all_gather(parts, self.vel, group=self.group)
+        return np.concatenate([p.to("cpu").numpy() for p in parts], axis=1).reshape(-1)
+
+    def close(self):
+        if not self.own:
+            return
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to go
+        for ptr in self.opened:
+            self.L.nb_ipc_close(self.C.c_void_p(ptr))
+        for ptr in self.own:
+            self.L.nb_dev_free(self.C.c_void_p(ptr))
+        self.L.nb_sym_destroy(self.h)
+        self.opened, self.own = [], []
+
+
+class SymLocalWorld:
+    """`world` ranks of the symmetric stepper on ONE GPU and one stream: every rank's acceleration kernel of a step is
+    enqueued before any rank's integrate kernel, so each in-kernel arrival wait is already satisfied when it is
+    reached.  Same kernels, same peer stores and counters as one process per GPU (the peers' buffers are ordinary
+    device pointers here): the multi-rank path, testable and checkable on a 1-GPU box."""
+
+    def __init__(self, system, world, device=None):
+        self.ranks = [SymShardedSystem(system, rank=r, world=world, device=device, _local_world=self) for r in range(world)]
+        peers = [list(r.own) for r in self.ranks]
+        for r in self.ranks:
+            r._connect(peers)
+        self.world = world
+
+    def advance(self, steps=1):
+        for _ in range(steps):
+            for r in self.ranks:
+                r.step_phase(1)
+            for r in self.ranks:
+                r.step_phase(2)
+
+    def positions(self):
+        return self.ranks[0].positions()
+
+    def velocities(self):
+        return np.concatenate([r.vel.detach().to("cpu").numpy() for r in self.ranks], axis=1).reshape(-1)
+
+    def close(self):
+        self.ranks[0].torch.cuda.synchronize()
+        for r in self.ranks:
+            r.world_for_close, r.world = r.world, 1  # no process group here
+            r.close()
+
+
 class ShardedSystem:
     def __init__(self, system, rank=0, world=1, device=None, math=0, group=None, local_step=None, step0=0):
         import torch

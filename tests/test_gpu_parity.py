@@ -394,18 +394,66 @@ def test_full_size_65536_one_step_against_oracle_and_invariants(nb, oracle):
     assert np.array_equal(v2, 2.0 * v)
 
 
+def close_states(q, v, qo, vo):
+    """FAST-math tolerance of SURVEY 8d C5: q within 1e-12*max|v|*dt (or 2 ulp), v within 1e-12 relative."""
+    return (np.abs(q - qo).max() <= max(1e-12 * np.abs(vo).max() * 60.0, 2 * np.spacing(np.abs(qo)).max())
+            and np.allclose(v, vo, rtol=1e-12, atol=0))
+
+
 def test_sharded_single_rank_matches_host_api(nb):
-    """The torch-plumbed device-pointer path (nb_large_pack / nb_large_step) == nb_run_steps."""
+    """The torch-plumbed device-pointer paths against nb_run_steps (which takes the symmetric stepper for FAST math):
+    SymShardedSystem is the same kernels -> bit for bit; ShardedSystem (row kernel, nb_large_pack / nb_large_step)
+    sums in another order -> FAST tolerance."""
     import torch
 
     n = 4096
     s = nb.synthetic_system(n, seed=11)
+    q, v = s.q.copy(), s.v.copy()
+    nb.run_steps(0, 5, n, q, v, s.m, s.is_device)
+    sy = nb.SymShardedSystem(s, rank=0, world=1, device="cuda:0")
+    sy.advance(5)
+    assert np.array_equal(sy.positions(), q) and np.array_equal(sy.velocities(), v)
+    sy.close()
     sh = nb.ShardedSystem(s, rank=0, world=1, device="cuda:0")
     sh.advance(5)
     torch.cuda.synchronize()
-    q, v = s.q.copy(), s.v.copy()
-    nb.run_steps(0, 5, n, q, v, s.m, s.is_device)
-    assert np.array_equal(sh.positions(), q) and np.array_equal(sh.velocities(), v)
+    assert close_states(sh.positions(), sh.velocities(), q, v)
+
+
+@pytest.mark.parametrize("n,world", [(6144, 2), (6144, 3), (6144, 4), (8192, 8), (3000, 1), (5000, 2)])
+def test_symmetric_stepper_multi_rank_on_one_gpu(nb, oracle, n, world):
+    """The multi-rank path of the symmetric stepper (block-pair assignment, partial rows stored into the owner's PJ,
+    arrival counters, in-kernel waits, pos4 rows stored into every rank) with all ranks on this GPU (SymLocalWorld):
+    against the CPU oracle at the FAST tolerance, run to run bit-identical, and no wait timed out (positions() checks
+    the status word).  Ragged shards (1500 = 1024 + 476 bodies) included."""
+    s = nb.synthetic_system(n, seed=17)
+    steps = 6
+    w = nb.SymLocalWorld(s, world, device="cuda:0")
+    w.advance(steps)
+    q, v = w.positions(), w.velocities()
+    for r in w.ranks[1:]:
+        assert np.array_equal(r.positions(), q), "every rank holds the same positions"
+    w.close()
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, n, qo, vo, s.m, s.is_device, 0, steps)
+    assert close_states(q, v, qo, vo)
+    w2 = nb.SymLocalWorld(s, world, device="cuda:0")
+    w2.advance(steps)
+    assert np.array_equal(w2.positions(), q) and np.array_equal(w2.velocities(), v), "deterministic"
+    w2.close()
+
+
+def test_symmetric_stepper_accelerations_ragged(nb, oracle):
+    """One step from rest (v = a*dt) on sizes that leave partial rows, partial j tiles and partial rotation groups."""
+    for n in (1025, 1500, 2049, 3333):
+        s = nb.synthetic_system(n, seed=n)
+        s.v[:] = 0.0
+        q, v = s.q.copy(), s.v.copy()
+        nb.run_steps(0, 1, n, q, v, s.m, s.is_device)
+        qo, vo = s.q.copy(), s.v.copy()
+        oracle.run_steps(oracle.MODE_STRICT, n, qo, vo, s.m, s.is_device, 0, 1)
+        scale = np.abs(vo.reshape(3, -1)).max(axis=0)
+        assert (np.abs(v - vo).reshape(3, -1) / scale).max() < 1e-12, n
 
 
 def test_p2p_fused_exchange_single_rank(nb):

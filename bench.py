@@ -65,25 +65,76 @@ def reference_run(case="b20"):
     return dt, steps * n * (n - 1), kind
 
 
+SAMPLE_N = 8192  # bodies of the bounded CPU sample of the synthetic workload
+
+
+def write_synthetic_input(path, n, seed=42):
+    """The synthetic workload's generator parameters (positions uniform in a 1e13 m cube centred at
+    (-2.0e20, -2.9e20, 1.8e18), velocities N(0, 1e7 m/s), masses log-uniform in [1e20, 1e30] kg, body 0 planet, body 1
+    asteroid, the last 4 bodies gravity devices) in the reference's input format (nbody.cc:22-39), pure Python: the
+    reference arm loads nothing of this repo's."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    q = np.array([-2.0e20, -2.9e20, 1.8e18]) + (rng.random((n, 3)) - 0.5) * 1e13
+    v = rng.normal(0.0, 1e7, (n, 3))
+    m = 10.0 ** (20.0 + 10.0 * rng.random(n))
+    with open(path, "w") as f:
+        f.write("%d 0 1\n" % n)
+        for i in range(n):
+            f.write("%.17g %.17g %.17g %.17g %.17g %.17g %.17g %s\n" % (*q[i], *v[i], m[i], "device" if i >= n - 4 else "star"))
+
+
+def reference_sample_run(n=SAMPLE_N, inp=None):
+    """run_step of the reference on a bounded sample of the SAME workload (a synthetic system of the same generator
+    parameters, n bodies): samples/nbody.cc with param::n_steps set to 1 at build time (oracle/Makefile pipes the
+    source through sed; nothing else differs), i.e. two run_step calls (query 1 and query 2, nbody.cc:116,129).
+    Returns (seconds, ordered pair interactions, kind)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "nbody_steps1")
+    kind = "reference"
+    args = []
+    if not os.path.exists(exe):
+        exe, kind, args = os.path.join(ROOT, "oracle", "_build", "nbody_oracle"), "port", ["1", "0", "1"]
+    own = inp is None
+    if own:
+        inp = "/tmp/bench_sample_%d_%d.in" % (n, os.getpid())
+        write_synthetic_input(inp, n)
+    out = "/tmp/bench_sample_%d.out" % os.getpid()
+    t0 = time.perf_counter()
+    subprocess.check_call([exe, inp, out] + args)
+    dt = time.perf_counter() - t0
+    if own:
+        os.unlink(inp)
+    return dt, 2 * n * (n - 1), kind
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    inp = "/tmp/bench_sample_%d_%d.in" % (SAMPLE_N, os.getpid())
+    write_synthetic_input(inp, SAMPLE_N)
     for _ in range(args.warmup):
-        reference_run()
+        reference_sample_run(inp=inp)
     tot_t, tot_p, kind = 0.0, 0, "reference"
     for _ in range(args.steps):
-        dt, pairs, kind = reference_run()
+        dt, pairs, kind = reference_sample_run(inp=inp)
         tot_t += dt
         tot_p += pairs
+    os.unlink(inp)
     val = tot_p / tot_t
-    sample = "full b20.in run of samples/nbody.cc (query 1 + query 2, 338 784 steps x 380 ordered pairs) per step"
+    sample = ("per step: two run_step calls (query 1 + query 2, param::n_steps = 1 set at build time) of samples/nbody.cc, "
+              "serial, on a %d-body synthetic system with the workload's generator parameters = %d ordered pairs; the "
+              "full 65536-body step would take ~200 s on one core (pairs/s does not depend on n: same loop)"
+              % (SAMPLE_N, 2 * SAMPLE_N * (SAMPLE_N - 1)))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "reference golden input b20.in",
-        "config": {"workload": "synthetic 65536-body single system (reference arm: bounded CPU sample, see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic 65536-body single system", "reference_arm_sample_bodies": SAMPLE_N,
+                   "same_config": "same workload and generator parameters, bounded to %d bodies per CPU step (see cpu_baseline.sample)" % SAMPLE_N},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,6 +253,102 @@ class ClockSampler:
                 "source": self.source}
 
 
+def close_states(np, q, v, qo, vo):
+    """FAST-math parity bar of SURVEY 8d C5: q within 1e-12*max|v|*dt (or 2 ulp), v within 1e-12 relative.
+    Returns (ok, max relative v difference, max absolute q difference)."""
+    dv = float(np.max(np.abs(v - vo) / np.maximum(np.abs(vo), 1e-300)))
+    dq = float(np.abs(q - qo).max())
+    ok = dq <= max(1e-12 * float(np.abs(vo).max()) * 60.0, 2 * float(np.spacing(np.abs(qo)).max())) and dv <= 1e-12
+    return bool(ok), dv, dq
+
+
+def make_system(nb, kind, system, rank, world, dev):
+    if kind == "sym":
+        return nb.SymShardedSystem(system, rank=rank, world=world, device=dev)
+    if kind == "p2p":
+        return nb.P2PShardedSystem(system, rank=rank, world=world, device=dev)
+    return nb.ShardedSystem(system, rank=rank, world=world, device=dev)
+
+
+def hw5_process_block(nb):
+    """The real `hw5 <input> <output>` PROCESS on b1024 (BASELINE metric (i)) next to the floor of any CUDA process on
+    this box (driver initialisation + one context + one empty kernel, tools/microbench/cuda_floor.cu)."""
+    pkg = os.path.dirname(nb.LIB_PATH)
+    exe, floor_exe = os.path.join(pkg, "hw5"), os.path.join(pkg, "cuda_floor")
+    inp, gold = os.path.join(CASES, "b1024.in"), open(os.path.join(CASES, "b1024.out"), "rb").read()
+    env = dict(os.environ, NB_VERBOSE="1")
+    env.pop("CUDA_VISIBLE_DEVICES", None)  # the binary narrows it itself (to GPU 0)
+    runs = []
+    for rep in range(2):
+        fl = None
+        if os.path.exists(floor_exe):
+            t0 = time.perf_counter()
+            r = subprocess.run([floor_exe], capture_output=True, env=env, timeout=120)
+            fl = {"wall_s": time.perf_counter() - t0}
+            try:
+                fl.update(json.loads(r.stdout.decode().strip().split("\n")[-1]))
+            except Exception:
+                pass
+        out = "/tmp/bench_hw5_%d.out" % os.getpid()
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, inp, out], capture_output=True, env=env, timeout=300)
+        wall = time.perf_counter() - t0
+        err = r.stderr.decode()
+        laps = {}
+        for ln in err.split("\n"):
+            if "start-up (driver" in ln:
+                laps["gpu_startup_s"] = float(ln.split()[-2])
+            elif "three queries (nb_solve)" in ln:
+                laps["solve_s"] = float(ln.split()[-2])
+            elif "chain plan" in ln and "kernels" in ln:
+                laps["kernels_s"] = float(ln.split("kernels")[-1].split()[0])
+            elif "read input" in ln:
+                laps["read_input_s"] = float(ln.split()[-2])
+        same = r.returncode == 0 and os.path.exists(out) and open(out, "rb").read() == gold
+        runs.append({"wall_s": wall, "rc": r.returncode, "byte_identical_to_golden": bool(same), "laps": laps, "cuda_floor": fl})
+    best = min(runs, key=lambda x: x["wall_s"])
+    return {"wall_s": best["wall_s"], "byte_identical_to_golden": all(x["byte_identical_to_golden"] for x in runs),
+            "kernels_s": best["laps"].get("kernels_s"), "gpu_startup_s": best["laps"].get("gpu_startup_s"),
+            "cuda_floor_s": best["cuda_floor"]["floor_s"] if best["cuda_floor"] and "floor_s" in best["cuda_floor"] else None,
+            "runs": runs,
+            "note": "process wall of the hw5 binary on one GPU (the CLI narrows CUDA_VISIBLE_DEVICES to GPU 0; the GPU is "
+                    "started on a helper thread while the input is parsed); cuda_floor = wall of a CUDA process that only "
+                    "initialises the driver, creates one context and launches one empty kernel on the same box: the part of "
+                    "the wall no CUDA program can avoid here"}
+
+
+def ensemble_block(nb, np, torch, dist, rank, world, local, dev, steps, systems):
+    """BASELINE config C4: `systems` independent 1024-body systems (member k = b1024.in with velocities scaled by
+    1 + 1e-9 k), `steps` steps, split over the ranks with no collective."""
+    base = nb.read_input(os.path.join(CASES, "b1024.in"))
+    mine = list(range(rank, systems, world))
+    S, n = len(mine), base.n
+    q = np.tile(base.q, (S, 1))
+    v = np.stack([base.v * (1 + 1e-9 * k) for k in mine])
+    m = np.tile(base.m, (S, 1))
+    isdev = np.tile(base.is_device, (S, 1))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ev, secs = nb.ensemble_run(q, v, m, isdev, [base.planet] * S, [base.asteroid] * S, kind=nb.KIND_Q2, step_end=steps, gpu=local)
+    wall = time.perf_counter() - t0
+    t = torch.tensor([secs, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = None
+    if rank == 0:  # member 0 is the golden system itself: its state must equal a plain trajectory's
+        tr = nb.Trajectory(base, nb.KIND_Q2, gpu=local)
+        tr.run(steps)
+        ok = bool(np.array_equal(tr.state()[0], q[0]))
+        tr.close()
+    pairs = systems * steps * n * (n - 1)
+    secs, wall = float(t[0]), float(t[1])
+    return {"workload": "synthetic ensemble of %d independent 1024-body systems, %d steps (config C4)" % (systems, steps),
+            "systems_per_rank": S, "gpu_s": secs, "wall_s_incl_copies": wall, "pairs_per_s": pairs / secs,
+            "frac_of_fp64_peak": pairs / secs * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
+            "member0_equals_single_trajectory": ok, "kernel": nb.ensemble_kernel_name() if hasattr(nb, "ensemble_kernel_name") else "traj_kernel"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -235,10 +382,7 @@ def run_ours(args):
 
     n = args.n
     system = nb.synthetic_system(n, seed=42)
-    if args.exchange == "p2p":
-        sh = nb.P2PShardedSystem(system, rank=rank, world=world, device=dev)
-    else:
-        sh = nb.ShardedSystem(system, rank=rank, world=world, device=dev)
+    sh = make_system(nb, args.exchange, system, rank, world, dev)
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
@@ -282,14 +426,29 @@ def run_ours(args):
     accel_ms, accel_n = nb.profile_read()
     nb.profile_enable(False)
     accel_ms = max_over_ranks(accel_ms / max(accel_n, 1))
-    flops_per_launch = PAIR_FLOPS * sh.i_count * (n - 1)
+    if args.exchange == "sym":
+        # ordered pairs one launch of this rank covers (2 x its unordered pairs + the one-sided diagonal rows, self pairs excluded)
+        rank_pairs = sh.pairs_per_step() - sh.i_count
+        kernel, instr_per_pair = "sym_accel_kernel", 10
+    else:
+        rank_pairs = sh.i_count * (n - 1)
+        kernel, instr_per_pair = "large_accel_kernel", 16
+    flops_per_launch = PAIR_FLOPS * rank_pairs
     achieved = flops_per_launch / (accel_ms * 1e-3) / 1e12
     peak_measured = nb.fp64_peak(local)
+    traffic, traffic_src = None, None
+    tfile = os.path.join(ROOT, "profiles", "r02_sym_accel_traffic.json")
+    if n == 65536 and world == 1 and args.exchange == "sym" and os.path.exists(tfile):
+        tj = json.load(open(tfile))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
 
-    # ---- end to end through the host-buffer operator ------------------------------------------------
-    qh = torch.from_numpy(system.q.copy()).pin_memory()
-    vh = torch.from_numpy(system.v.reshape(3, n)[:, sh.i_begin:sh.i_begin + sh.i_count].copy()).pin_memory()
-    e2e_sys = nb.ShardedSystem(system, rank=rank, world=world, device=dev)
+    # ---- end to end through the host-buffer operator (same kernels, same exchange as `value`) --------
+    ib, ic = sh.i_begin, sh.i_count
+    qh = torch.from_numpy(system.q.reshape(3, n)[:, ib:ib + ic].copy()).pin_memory()
+    vh = torch.from_numpy(system.v.reshape(3, n)[:, ib:ib + ic].copy()).pin_memory()
+    e2e_sys = make_system(nb, args.exchange, system, rank, world, dev)
+    if args.exchange != "sym":  # the row-kernel drivers take all positions from the host
+        qh = torch.from_numpy(system.q.copy()).pin_memory()
     for _ in range(args.warmup):
         h2d, d2h = e2e_sys.step_host(qh, vh)
     barrier()
@@ -303,8 +462,59 @@ def run_ours(args):
     e2e_wall = max_over_ranks(time.perf_counter() - te0)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = pairs_per_step * args.steps / max(e2e_ms * 1e-3, e2e_wall if world == 1 else 0.0)
-    # the e2e path must produce the same state as the resident path after the same number of steps
+    e2e_q_own = qh.numpy().copy() if args.exchange == "sym" else None
     launches_total = nb.kernel_launches()
+
+    # ---- parity of exactly what was timed (outside the timed regions) -------------------------------
+    parity = None
+    if not args.no_parity:
+        K = 3
+        a = make_system(nb, args.exchange, system, rank, world, dev)
+        a.advance(K)
+        qa, va = a.positions(), a.velocities()
+        b = make_system(nb, args.exchange, system, rank, world, dev)
+        b.advance(K)
+        qb, vb = b.positions(), b.velocities()
+        deterministic = bool(np.array_equal(qa, qb) and np.array_equal(va, vb))
+        c = nb.ShardedSystem(system, rank=rank, world=world, device=dev)  # row kernel + NCCL all-gather: independent path
+        c.advance(K)
+        torch.cuda.synchronize()
+        qc, vc = c.positions(), c.velocities()
+        ok_row, dv_row, dq_row = close_states(np, qa, va, qc, vc)
+        q1, v1 = system.q.copy(), system.v.copy()
+        nb.run_steps(0, K, n, q1, v1, system.m, system.is_device, gpu=local)  # one rank, one GPU, host-buffer operator
+        ok_one, dv_one, dq_one = close_states(np, qa, va, q1, v1)
+        # the e2e arm advanced warmup + steps steps from the same seed state through host buffers: same state as the
+        # resident arm after as many steps
+        e2e_ok = None
+        if e2e_q_own is not None:
+            d = make_system(nb, args.exchange, system, rank, world, dev)
+            d.advance(args.warmup + args.steps)
+            qd = d.positions().reshape(3, n)[:, ib:ib + ic]
+            e2e_ok = bool(np.array_equal(qd, e2e_q_own))
+            d.close() if hasattr(d, "close") else None
+        flags = torch.tensor([deterministic, ok_row, ok_one, 1 if e2e_ok in (None, True) else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        parity = {"steps": K, "run_to_run_bit_identical": bool(flags[0]), "vs_row_kernel_nccl_path": bool(flags[1]),
+                  "vs_row_kernel_max_rel_dv": dv_row, "vs_one_rank_run_steps": bool(flags[2]), "vs_one_rank_max_rel_dv": dv_one,
+                  "vs_one_rank_bit_identical": bool(np.array_equal(qa, q1) and np.array_equal(va, v1)),
+                  "e2e_state_equals_resident_state": bool(flags[3]), "exchange_status_word": 0,
+                  "tolerance": "v within 1e-12 relative, q within max(1e-12*max|v|*dt, 2 ulp) (SURVEY 8d C5); positions() raises if a peer wait timed out",
+                  "all_ranks": True}
+        if world == 1 and args.exchange == "sym":
+            emu = {}
+            for w in (2, 8):
+                lw = nb.SymLocalWorld(system, w, device=dev)
+                lw.advance(K)
+                okw, dvw, _ = close_states(np, lw.positions(), lw.velocities(), qa, va)
+                lw.close()
+                emu["world_%d" % w] = {"ok": okw, "max_rel_dv": dvw}
+            parity["multi_rank_path_emulated_on_this_gpu"] = emu
+        for x in (a, b):
+            x.close() if hasattr(x, "close") else None
+    for x in (sh, e2e_sys):
+        x.close() if hasattr(x, "close") else None
 
     # ---- b1024 three-query end to end (the other half of the BASELINE metric) -----------------------
     b1024 = None
@@ -321,52 +531,123 @@ def run_ours(args):
         ok = tl[1] == gl[1] and tl[2] == gl[2] and abs(float(tl[0]) - float(gl[0])) <= 1e-6 * float(gl[0])
         b1024 = {"solve_wall_s": wall, "gpu_s": gsecs, "pairs_per_s_gpu": pairs / gsecs if gsecs else None,
                  "trajectories": ans.n_trajectories, "matches_golden": bool(ok), "line1_byte_identical": tl[0] == gl[0],
+                 "us_per_step_q1": None,
                  "note": "in-process solve (contexts already created); as many GPUs as trajectories: Q1, Q2 and one Q3 trajectory per device from step 0, one per rank; fewer: Q1 on rank 0, Q2 -> Q3 candidates forked from Q2 on rank 1 (chain plan, nb_host.cu)"}
+        if rank == 0 and not args.no_hw5_process:
+            b1024["hw5_process"] = hw5_process_block(nb)
+        barrier()
 
-    # ---- CPU baseline: the unmodified reference program on this box's host cores --------------------
+    # ---- config C4: the synthetic ensemble ----------------------------------------------------------
+    ensemble = None
+    if not args.no_ensemble:
+        ensemble = ensemble_block(nb, np, torch, dist, rank, world, local, dev, args.ensemble_steps, args.systems)
+
+    # ---- CPU baselines on this box's host cores (N = 1 only) ----------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        dt, pairs, kind = reference_run()
+        dt, pairs, kind = reference_sample_run()
         cpu = {"value": pairs / dt, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
-               "sample": "one full b20.in run of samples/nbody.cc, serial (query 1 + query 2: 338 784 steps x 380 ordered pairs)",
-               "host_cores_available": os.cpu_count()}
+               "sample": "two run_step calls (param::n_steps = 1 set at build time) of samples/nbody.cc, serial, on a %d-body "
+                         "synthetic system with the workload's generator parameters (%d ordered pairs)" % (SAMPLE_N, pairs),
+               "host_cores_available": os.cpu_count(), "extras": cpu_extras(nb, np, system, args)}
 
     if rank == 0:
+        exch = {"sym": "symmetric stepper: partial accelerations and pos4 rows stored straight into the owners' / every rank's memory "
+                       "(peer-mapped buffers), in-kernel arrival waits, 2 launches per step, no NCCL on the data path",
+                "p2p": "row kernel, P2P stores fused into the integrate kernel (peer-mapped buffers, no NCCL on the data path)",
+                "nccl": "row kernel, in-place NCCL all-gather of pos4 rows"}[args.exchange]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic 65536-body single system, body-sharded, per-step pos4 all-gather" if n == 65536
-                       else "synthetic %d-body single system, body-sharded" % n,
+            "config": {"workload": "synthetic 65536-body single system" if n == 65536 else "synthetic %d-body single system" % n,
                        "n_bodies": n, "seed": 42, "bodies_per_rank": sh.i_count, "pairs_per_step": pairs_per_step,
-                       "math": "fast (16 FP64 instr/pair)", "parallelism": "body-sharded x%d" % world,
-                       "exchange": ("P2P stores fused into the integrate kernel (peer-mapped buffers, no NCCL on the data path)"
-                                    if args.exchange == "p2p" else "in-place NCCL all-gather of pos4 rows") if world > 1 else "none (1 GPU)",
+                       "math": "fast; every unordered pair evaluated once, both accelerations accumulated (10 FP64 instr per ordered pair)"
+                               if args.exchange == "sym" else "fast (16 FP64 instr per ordered pair)",
+                       "parallelism": "body-sharded x%d" % world, "exchange": exch if world > 1 else "none (1 GPU)",
                        "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB memset, outside the per-step events)",
                        "exchange_bytes_per_rank_per_step": sh.bytes_exchanged_per_step()},
             "frac_of_fp64_peak": value * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_NOMINAL_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_NOMINAL_TFLOPS,
-                         "traffic": 2.88e6 if (n == 65536 and world == 1) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
-                                           "profiles/r01_large_accel_kernel.ncu-rep (n = 65536, 1 GPU)",
-                         "kernel": "large_accel_kernel", "kernel_ms": accel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kernel, "kernel_ms": accel_ms,
                          "peak_source": "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP64 entry)",
                          "peak_measured_dfma": peak_measured, "frac_of_measured": achieved / peak_measured,
-                         "flops_per_pair": PAIR_FLOPS, "fp64_instr_per_pair": 16,
+                         "flops_per_pair": PAIR_FLOPS, "fp64_instr_per_pair": instr_per_pair,
+                         "ordered_pairs_per_launch": rank_pairs,
                          "note": "compute-bound path: algorithmic bytes are 104 B x n per step (intensity ~12600 flop/B), "
-                                 "so the roofline is the FP64 pipe, not HBM or tensor cores (SURVEY.md 8d)"},
+                                 "so the roofline is the FP64 pipe, not HBM or tensor cores (SURVEY.md 8d); achieved = 20 flop x "
+                                 "ordered pairs per launch / CUDA-event duration of the kernel"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "per rank per step: this rank's positions and velocities host -> device (pinned), published to every "
+                            "rank, the step's kernels, the new rows device -> host; same kernels and exchange as `value`"},
             "gpu_launches": launches,
             "gpu_launches_total_process": launches_total,
             "clocks": clocks,
+            "parity": parity,
             "cpu_baseline": cpu,
             "b1024": b1024,
+            "ensemble": ensemble,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_extras(nb, np, system, args):
+    """BASELINE.md section 4 items 2-4, each bounded."""
+    ex = {}
+    try:
+        dt, pairs, kind = reference_run("b20")
+        ex["b20_full"] = {"seconds": dt, "pairs_per_s": pairs / dt, "cores": 1, "kind": kind,
+                          "what": "full b20.in run of the unmodified samples/nbody.cc (query 1 + query 2), output lines 1-2 equal the golden"}
+    except Exception as e:  # noqa: BLE001
+        ex["b20_full"] = {"error": str(e)}
+    exe = os.path.join(ROOT, "oracle", "_ref", "nbody_steps200")
+    if os.path.exists(exe):
+        out = "/tmp/bench_w200_%d.out" % os.getpid()
+        t0 = time.perf_counter()
+        subprocess.check_call([exe, os.path.join(CASES, "b1024.in"), out])
+        dt = time.perf_counter() - t0
+        pairs = 2 * 200 * 1024 * 1023  # query 1 and query 2, 200 steps each (no hit that early)
+        full_pairs = (200000 + 148198) * 1024 * 1023  # nbody.cc runs Q1 to the end and Q2 to the hit step (golden: 148198)
+        ex["b1024_window_200_steps"] = {"seconds": dt, "pairs_per_s": pairs / dt, "cores": 1, "kind": "reference",
+                                        "extrapolated_full_b1024_q1_q2_seconds": full_pairs / (pairs / dt),
+                                        "what": "samples/nbody.cc with param::n_steps = 200 (set at build time) on b1024.in; the full "
+                                                "Q1 + Q2 run is EXTRAPOLATED linearly from this window"}
+    # the repo's CPU oracle (OpenMP over i, bit-identical to serial) on all host cores: one step of the 65536-body system,
+    # which is also the full-size parity check of the GPU step
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as orc
+
+        n = system.n
+        cores = os.cpu_count()
+        if cores >= 16 and not args.no_oracle_full_step:
+            qo, vo = system.q.copy(), system.v.copy()
+            t0 = time.perf_counter()
+            orc.run_steps(orc.MODE_SQRT3, n, qo, vo, system.m, system.is_device, 0, 1, nthreads=cores)
+            dt = time.perf_counter() - t0
+            q, v = system.q.copy(), system.v.copy()
+            nb.run_steps(0, 1, n, q, v, system.m, system.is_device, gpu=0)
+            ok, dv, dq = close_states(np, q, v, qo, vo)
+            ex["openmp_oracle_65536_one_step"] = {"seconds": dt, "pairs_per_s": n * (n - 1) / dt, "cores": cores, "kind": "port",
+                                                  "gpu_step_matches": ok, "max_rel_dv": dv, "max_abs_dq_m": dq,
+                                                  "what": "oracle/nbody_oracle.cc, sqrt(r2^3) mode, OpenMP over i on all host cores"}
+        else:
+            ns = 16384
+            sub = nb.synthetic_system(ns, seed=42)
+            qo, vo = sub.q.copy(), sub.v.copy()
+            t0 = time.perf_counter()
+            orc.run_steps(orc.MODE_SQRT3, ns, qo, vo, sub.m, sub.is_device, 0, 1, nthreads=cores)
+            dt = time.perf_counter() - t0
+            ex["openmp_oracle_16384_one_step"] = {"seconds": dt, "pairs_per_s": ns * (ns - 1) / dt, "cores": cores, "kind": "port",
+                                                  "what": "fewer than 16 host cores: one step of a 16384-body system instead of 65536"}
+    except Exception as e:  # noqa: BLE001
+        ex["openmp_oracle"] = {"error": str(e)}
+    return ex
 
 
 def run_ensemble(args):
@@ -449,8 +730,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--workload", default="large", choices=["large", "ensemble"])
-    ap.add_argument("--exchange", default=os.environ.get("NB_EXCHANGE", "p2p"), choices=["nccl", "p2p"])
+    ap.add_argument("--exchange", default=os.environ.get("NB_EXCHANGE", "sym"), choices=["sym", "nccl", "p2p"])
     ap.add_argument("--systems", type=int, default=1024)
+    ap.add_argument("--ensemble-steps", type=int, default=10000)
+    ap.add_argument("--no-ensemble", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-hw5-process", action="store_true")
+    ap.add_argument("--no-oracle-full-step", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

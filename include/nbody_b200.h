@@ -166,8 +166,15 @@ int nb_write_input(const char* path, int n, int planet, int asteroid, const doub
  * n_devices bodies are gravity devices.  q, v: [3n] planar; m, is_device: [n]. */
 int nb_generate_system(int n, unsigned long long seed, int n_devices, double* q, double* v, double* m,
                        unsigned char* is_device, int* planet, int* asteroid);
-/* the whole CLI: hw5 <input> <output> (hw5.cu:532-616) */
+/* the whole CLI: hw5 <input> <output> (hw5.cu:532-616).  The GPUs (n_gpus, or NB_HW5_GPUS, default 1) are started on
+ * helper threads while the input is parsed (hw5.cu:555-567 starts its two GPUs from parallel host threads). */
 int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus);
+/* process start-up helpers: nb_device_warm = driver initialisation + context + constant tables + kernel module of one
+ * GPU (thread-safe; call it early, from a helper thread); nb_hw5_narrow_visible_gpus sets CUDA_VISIBLE_DEVICES to the
+ * first `want` GPUs unless the user set it - it changes the PROCESS environment, so only the `hw5` binary's main()
+ * calls it, before the first CUDA call, never the library itself.  Returns the number of /dev/nvidiaN nodes, or -1. */
+int nb_device_warm(int gpu);
+int nb_hw5_narrow_visible_gpus(int want);
 
 /* ---- large systems, body-sharded (north-star (d)) -------------------------------------------
  * DEVICE-pointer interface: the caller (C++ or torch) owns the buffers and the stream, so that a
@@ -221,7 +228,8 @@ int nb_ipc_close(void* dev_ptr);
  * UNORDERED pair evaluated once: both a_i and a_j are accumulated, 10 FP64 instructions per ordered pair.
  * Rank r of `world` holds shard [r*n/world, (r+1)*n/world) and evaluates the block pairs (r, r) .. (r, r + world/2);
  * the partial accelerations of a body are stored straight into the memory of the rank that owns it (PJ, a
- * peer-mapped buffer of nb_sym_pj_bytes() bytes per rank) and its integrate kernel sums them in a fixed order,
+ * peer-mapped buffer of nb_sym_pj_bytes() bytes per rank, ZERO-FILLED once: rows nobody writes are summed as zeros)
+ * and its integrate kernel sums them in a fixed order,
  * integrates and stores the new pos4 record into EVERY rank's next-step buffer.  Arrival is signalled through
  * per-rank counter blocks (nb_sym_counter_bytes() bytes, zeroed, peer-mapped) with system-scope release/acquire;
  * the kernels wait on them in-kernel, so a step is two launches and no host synchronisation or NCCL call.
@@ -247,6 +255,14 @@ int nb_sym_step(nb_sym* h, int step, const double* pos4_cur_dev, double* const* 
 int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur_dev, double* const* peer_pos4_next,
                       double* const* peer_pj, unsigned long long* const* peer_counters, int* status_dev,
                       double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* stream);
+/* run_step with HOST buffers, sharded (bench "e2e"): nb_sym_publish_rows turns this rank's positions (planar
+ * [3][n/world] doubles on the device, just copied from the host) into pos4 records {x, y, z, G*m_eff(step_next)} in EVERY
+ * rank's current buffer, signalled like the integrate kernel's stores (every rank must call it before the same step);
+ * nb_sym_unpack_rows extracts this rank's rows of a pos4 buffer back into planar form for the copy to the host. */
+int nb_sym_publish_rows(nb_sym* h, int step_next, const double* q_own_planar_dev, double* const* peer_pos4_cur,
+                        unsigned long long* const* peer_counters, const double* m0_dev,
+                        const unsigned char* is_device_dev, void* stream);
+int nb_sym_unpack_rows(nb_sym* h, const double* pos4_dev, double* q_own_planar_dev, void* stream);
 /* The static schedule of one rank (host only, no GPU needed): segments of eight ints
  * {row_body0, row_count, j0, j1, flags, pi_slot, pj_row, src_rank} (flags: 1 = one-sided, 2 = load row, 4 = flush row),
  * block b owns segments [block_seg_begin[b], block_seg_begin[b+1]); pj_ptr / pj_list = per local row the PJ rows
@@ -254,7 +270,8 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur_de
 int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, int* segs_out, int* n_segs,
                          int* block_seg_begin, int* pj_ptr, int* pj_list, int max_pj, long long* sym_pairs,
                          long long* onesided_pairs);
-int nb_sym_rows(int n, int world); /* rows (superblocks of 1024 bodies) per rank */
+int nb_sym_row_size(void);         /* bodies per row (= i-bodies per thread block) of this build */
+int nb_sym_rows(int n, int world); /* rows per rank */
 
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */

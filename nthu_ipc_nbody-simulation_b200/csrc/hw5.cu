@@ -2,6 +2,7 @@
 #include <unistd.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "../../include/nbody_b200.h"
@@ -10,6 +11,10 @@ int main(int argc, char** argv) {
     if (argc != 3) {
         throw std::runtime_error("must supply 2 arguments");  // hw5.cu:533-535
     }
+    // before the first CUDA call: the driver initialises every VISIBLE GPU (0.6-0.9 s each on the B200 boxes)
+    const int want = getenv("NB_HW5_GPUS") ? atoi(getenv("NB_HW5_GPUS")) : 1;
+    nb_hw5_narrow_visible_gpus(want < 1 ? 1 : want);
+    setenv("NB_HW5_FAST_EXIT", "1", 0);  // this process ends in _exit below: the library need not free anything
     int rc = nb_hw5_main(argv[1], argv[2], 0);
     if (rc != NB_OK) {
         fprintf(stderr, "hw5: %s: %s\n", nb_strerror(rc), nb_last_error_detail());

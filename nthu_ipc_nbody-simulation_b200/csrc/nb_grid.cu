@@ -56,6 +56,7 @@
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <set>
 #include <string>
@@ -716,23 +717,31 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     attrs[1].val.cooperative = 1;
     cfg.attrs = attrs, cfg.numAttrs = 2;
     {   // function attributes and the co-residency check: once per (device, kernel, shape) - the chain plan of
-        // nb_solve launches this kernel every NB_SOLVE_CHUNK steps
+        // nb_solve launches this kernel every NB_SOLVE_CHUNK steps.  The dynamic shared-memory limit is an attribute of
+        // the kernel FUNCTION (every call overwrites it), so it is only ever raised: a per-(device, kernel) running
+        // maximum, else b1024 -> b512 -> b1024 in one process would launch 160 KB against a limit lowered to 80 KB.
         static std::mutex mu;
         static std::set<std::tuple<int, const void*, size_t, int, int>> checked;
+        static std::map<std::pair<int, const void*>, size_t> smem_limit;
         int dev = 0;
         NB_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lk(mu);
+        size_t& limit = smem_limit[std::make_pair(dev, (const void*)kern)];
+        if (smem > limit) {
+            NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            limit = smem;
+        }
         const auto key = std::make_tuple(dev, (const void*)kern, smem, cs, C);
         if (!checked.count(key)) {
-            NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (cs > 8) NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             int max_clusters = 0;
             NB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            static const bool force_unsupported = env_int("NB_GRID_FORCE_UNSUPPORTED", 0) != 0;  // tests: the fallback path
+            if (force_unsupported) max_clusters = 0;
             if (max_clusters < C / cs) {
                 set_error_detail("grid trajectory kernel: " + std::to_string(C / cs) + " clusters of " + std::to_string(cs) +
-                                 " blocks are not co-resident on this GPU (max " + std::to_string(max_clusters) +
-                                 "); set NB_GRID_CS lower");
-                return NB_ERR_UNSUPPORTED;
+                                 " blocks are not co-resident on this GPU (max " + std::to_string(max_clusters) + ")");
+                return NB_ERR_UNSUPPORTED;  // nothing has been launched: the caller may try a smaller cluster or another kernel
             }
             checked.insert(key);
         }
@@ -820,6 +829,12 @@ bool grid_traj_supported(int gpu, int n, int n_traj) {
     return true;
 }
 
+void grid_traj_warm() {
+    cudaFuncAttributes fa;
+    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 1, 4, false>);
+    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 2, 4, false>);
+}
+
 // device address of the status word of a workspace: 0 = ok, 1 = an exchange spin timed out (read after the stream is idle)
 const int* grid_traj_status(const void* ws, int n) { return (const int*)((const char*)ws + ws_layout(n, MAX_T).gbuf_bytes); }
 
@@ -832,13 +847,18 @@ int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs, const d
     if (ws_bytes < ws_layout(n, MAX_T).total) return NB_ERR_ARG;
     // STRICT never comes here: its ascending-j sum is the single-block kernel's (nb_host.cu)
     if (math != NB_MATH_FAST) return NB_ERR_UNSUPPORTED;
-    const int cs = cluster_size_for(n);
-    const int G = group_size(n, cs);
     NB_CUDA(cudaMemsetAsync((char*)ws + ws_layout(n, MAX_T).gbuf_bytes, 0, 64, stream));  // status word, sticky over the groups
-    for (int t0 = 0; t0 < n_traj; t0 += G) {  // groups of up to G trajectories run in lock step
-        const int T = n_traj - t0 < G ? n_traj - t0 : G;
-        int rc = launch_m<MATH_FAST>(T, n, cs, descs + t0, fst, ws, stream);
-        if (rc) return rc;
+    // clusters that are not co-resident (MIG / MPS / a shared GPU): halve the cluster size; NB_ERR_UNSUPPORTED comes back
+    // before anything has been launched, and with clusters of 1 it goes up to the caller, who has the single-block kernel
+    for (int cs = cluster_size_for(n);; cs >>= 1) {
+        const int G = group_size(n, cs);
+        int rc = NB_OK;
+        for (int t0 = 0; t0 < n_traj && rc == NB_OK; t0 += G) {  // groups of up to G trajectories run in lock step
+            const int T = n_traj - t0 < G ? n_traj - t0 : G;
+            rc = launch_m<MATH_FAST>(T, n, cs, descs + t0, fst, ws, stream);
+            if (rc == NB_ERR_UNSUPPORTED && t0 > 0) return NB_ERR_CUDA;  // cannot happen: the first group decides
+        }
+        if (rc != NB_ERR_UNSUPPORTED || cs == 1) return rc;
     }
     return NB_OK;
 }

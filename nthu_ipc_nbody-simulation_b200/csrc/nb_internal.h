@@ -51,5 +51,6 @@ int launch_grid_traj(int math, int n, int n_traj, const TrajDesc* descs_dev, con
 size_t grid_traj_workspace_bytes(int n, int n_traj);
 const int* grid_traj_status(const void* workspace_dev, int n);  // sticky status word, read it once the stream is idle
 bool grid_traj_supported(int gpu, int n, int n_traj);
+void grid_traj_warm();  // loads the kernels' module on the current device (lazy loading would do it at the first launch)
 
 }  // namespace nb

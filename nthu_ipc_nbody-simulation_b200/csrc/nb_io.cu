@@ -15,6 +15,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nb_internal.h"
@@ -93,6 +94,10 @@ int nb_read_input(const char* path, int max_n, int* n, int* planet, int* asteroi
         return NB_ERR_IO;
     }
     if (a > max_n) return NB_ERR_ARG;
+    if (b < 0 || b >= a || d < 0 || d >= a) {  // the reference indexes its arrays with them unchecked (nbody.cc:118-120)
+        nb::set_error_detail(std::string("planet / asteroid index out of range in ") + path);
+        return NB_ERR_IO;
+    }
     const int nn = (int)a;
     *n = nn, *planet = (int)b, *asteroid = (int)d;
     for (int i = 0; i < nn; i++) {
@@ -182,6 +187,22 @@ static int count_gpus_procfs() {
     return cnt;
 }
 
+// Start-up path of the `hw5` PROCESS only (csrc/hw5.cu calls it before the first CUDA call; the library itself never
+// touches the environment): narrows CUDA_VISIBLE_DEVICES to the first `want` GPUs.  Returns the number of GPUs found.
+int nb_hw5_narrow_visible_gpus(int want) {
+    if (getenv("CUDA_VISIBLE_DEVICES") || want < 1) return -1;  // the user's choice wins
+    const int present = count_gpus_procfs();
+    if (present > 0 && want < present) {
+        std::string list;
+        for (int g = 0; g < want; g++) list += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+        if (getenv("NB_VERBOSE")) fprintf(stderr, "nbody_b200: %d GPUs present, using CUDA_VISIBLE_DEVICES=%s\n", present, list.c_str());
+    }
+    return present;
+}
+
+void nb_internal_leak_on_exit(int on);  // nb_host.cu
+
 // hw5 <input> <output> (hw5.cu:532-616)
 int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
     const bool verbose = getenv("NB_VERBOSE") != nullptr;
@@ -193,43 +214,54 @@ int nb_hw5_main(const char* input_path, const char* output_path, int n_gpus) {
             t0 = t1;
         }
     };
+    // Start-up path (the reference starts its two GPUs from parallel host threads, hw5.cu:555-567):
+    // driver initialisation, context creation, the |sin| table upload and the kernel module load of every GPU that will be
+    // used run on helper threads WHILE this thread parses the input; nothing below waits for them before it has to.
+    if (n_gpus <= 0) n_gpus = getenv("NB_HW5_GPUS") ? atoi(getenv("NB_HW5_GPUS")) : 1;
+    if (n_gpus < 1) n_gpus = 1;
+    std::vector<std::thread> warm;
+    std::vector<double> warm_s(n_gpus, 0.0);
+    for (int g = 0; g < n_gpus; g++)
+        warm.emplace_back([g, &warm_s] {
+            const auto w0 = std::chrono::steady_clock::now();
+            nb_device_warm(g);  // a GPU that does not exist fails here silently and loudly in nb_solve
+            warm_s[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+        });
+    auto join_warm = [&] {
+        for (auto& t : warm)
+            if (t.joinable()) t.join();
+    };
     int n, planet, asteroid;
     int rc = nb_read_header(input_path, &n, &planet, &asteroid);
-    if (rc) return rc;
+    if (rc) {
+        join_warm();
+        return rc;
+    }
     std::vector<double> q(3 * (size_t)n), v(3 * (size_t)n), m(n);
     std::vector<unsigned char> dev(n);
     rc = nb_read_input(input_path, n, &n, &planet, &asteroid, q.data(), v.data(), m.data(), dev.data());
+    lap("read input (beside the GPU start-up)");
+    join_warm();
     if (rc) return rc;
-    lap("read input");
+    if (verbose)
+        for (int g = 0; g < n_gpus; g++) fprintf(stderr, "nbody_b200: gpu %d start-up (driver + context + tables + module) %.3f s\n", g, warm_s[g]);
     int n_traj = 2;
     for (int i = 0; i < n; i++) n_traj += dev[i] ? 1 : 0;
     // How many GPUs: the driver initialises every VISIBLE device (0.6-0.9 s each on the B200 boxes, 2.0-2.6 s for four) and
-    // a context costs another 0.6-1.6 s per used GPU, while the kernels of b1024 take 1.11 s on one GPU, 0.73 s on two and
-    // 0.65 s on four (chain / independent plan, nb_host.cu).  Measured end to end on a 2-GPU box: one GPU 2.5-3.2 s, two
-    // GPUs 3.1-3.5 s - the second context costs more than its kernels save, so the CLI uses ONE GPU unless told otherwise
-    // (NB_HW5_GPUS, or the n_gpus argument of nb_hw5_main).
-    if (n_gpus <= 0) n_gpus = getenv("NB_HW5_GPUS") ? atoi(getenv("NB_HW5_GPUS")) : 1;
-    if (n_gpus < 1) n_gpus = 1;
+    // a context costs another 0.6-1.6 s per used GPU, while the kernels of b1024 take ~1 s on one GPU and ~0.6 s on two or
+    // four (chain / independent plan, nb_host.cu).  Measured end to end on a 2-GPU box: the second context costs more than
+    // its kernels save, so the CLI uses ONE GPU unless told otherwise (NB_HW5_GPUS, or the n_gpus argument).
     if (n_gpus > n_traj) n_gpus = n_traj;
-    if (!getenv("CUDA_VISIBLE_DEVICES")) {
-        const int present = count_gpus_procfs();
-        const int want = n_gpus;
-        if (present > 0 && want < present) {
-            std::string list;
-            for (int g = 0; g < want; g++) list += (g ? "," : "") + std::to_string(g);
-            setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
-            if (verbose) fprintf(stderr, "nbody_b200: %d GPUs present, using CUDA_VISIBLE_DEVICES=%s\n", present, list.c_str());
-        }
-    }
     {
         int have = 0;
         rc = nb_device_count(&have);
         if (rc) return rc;
         if (n_gpus > have) n_gpus = have;
     }
-    lap("driver initialisation");
+    lap("wait for the GPU start-up");
     nb_system sys{n, planet, asteroid, q.data(), v.data(), m.data(), dev.data()};
     nb_answer ans;
+    if (getenv("NB_HW5_FAST_EXIT")) nb_internal_leak_on_exit(1);  // set by the hw5 binary: it leaves through _exit
     rc = nb_solve(&sys, nullptr, n_gpus, NB_N_STEPS, NB_MATH_FAST, &ans);
     if (rc) return rc;
     lap("three queries (nb_solve)");

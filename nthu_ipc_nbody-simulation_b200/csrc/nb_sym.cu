@@ -2,7 +2,7 @@
 // so an ordered pair interaction costs 10 FP64-pipe instructions instead of 16 (nb_large.cu) or the reference's
 // 29 + 3 atomics (hw5.cu:159-215).  Arithmetic: nbody.cc:56-88; every ordered pair of run_step still contributes.
 //
-//   * A block owns a ROW of SB = 1024 consecutive bodies, 4 per lane, in registers {x, y, z, G*m, ax, ay, az}.
+//   * A block owns a ROW of SB = 1536 consecutive bodies, 6 per lane, in registers {x, y, z, G*m, ax, ay, az}.
 //   * j bodies stream through shared memory in tiles of TJ records (1-D TMA bulk copies, mbarrier ring).  A warp
 //     takes 32 of them, one per lane, and ROTATES them through its lanes with warp shuffles: after 32 rotations
 //     every lane has met every j body, and the j body has collected its own acceleration {ajx, ajy, ajz} in
@@ -12,7 +12,7 @@
 //     these stores); a_i leaves once per row run as PI[slot][3][SB].  sym_integrate_kernel sums the partials of a
 //     body in a fixed order (deterministic, no atomics), integrates and publishes the new pos4 record to every rank.
 //   * The work (upper triangle of the row x j-group matrix) is cut into equal-cost pieces on the host
-//     (build_plan): a static schedule, one piece per resident block, granularity 1024 x 32 pairs.
+//     (build_plan): a static schedule, one piece per resident block, granularity 1536 x 32 pairs.
 //   * Multi-GPU: rank p holds shard p and evaluates the block pairs (p, p), (p, p+1) .. (p, p+P/2) (the last one
 //     split in half for even P), local work first, so that the peers' positions arrive behind it.
 #include <algorithm>
@@ -27,16 +27,23 @@
 #include "nb_math.cuh"
 #include "nb_sym.cuh"
 
+#ifndef NB_SYM_EXP
+#define NB_SYM_EXP 0
+#endif
+#ifndef NB_SYM_UNROLL
+#define NB_SYM_UNROLL 2
+#endif
+
 namespace nb {
 namespace sym {
 
 // ================================================================================================ planner (host)
 namespace {
 struct Span {
-    int row;   // local row
-    int j0, j1;
+    int i0, icount;  // the row: local bodies [i0, i0 + icount) of the rank (at most SB; aligned rows start at a multiple of SB)
+    int j0, j1;      // global j range
     bool onesided;
-    int src;
+    int src;         // rank that owns [j0, j1)
 };
 
 int rows_of(int shard) { return (shard + SB - 1) / SB; }
@@ -44,28 +51,36 @@ int rows_of(int shard) { return (shard + SB - 1) / SB; }
 // the spans of rank p, phase by phase (phase 0 = local, phase 1 = remote)
 void spans_of_rank(int n, int world, int p, std::vector<std::vector<Span>>& phases) {
     const int S = n / world, R = rows_of(S), base = p * S;
+    auto cnt = [&](int r) { return std::min(S, (r + 1) * SB) - r * SB; };
     phases.assign(2, {});
     for (int r = 0; r < R; r++) {
-        const int r0 = base + r * SB, r1 = base + std::min(S, (r + 1) * SB);
-        if (r1 < base + S) phases[0].push_back({r, r1, base + S, false, p});  // the rows behind it, symmetric
-        phases[0].push_back({r, r0, r1, true, p});                            // its own bodies, one-sided
+        const int r1 = std::min(S, (r + 1) * SB);
+        if (r1 < S) phases[0].push_back({r * SB, cnt(r), base + r1, base + S, false, p});  // the rows behind it, symmetric
+        phases[0].push_back({r * SB, cnt(r), base + r * SB, base + r1, true, p});           // its own bodies, one-sided
     }
     if (world == 1) return;
     const int full = (world - 1) / 2;  // partners evaluated entirely by this rank
     for (int k = 1; k <= full; k++) {
         const int q = (p + k) % world;
-        for (int r = 0; r < R; r++) phases[1].push_back({r, q * S, q * S + S, false, q});
+        for (int r = 0; r < R; r++) phases[1].push_back({r * SB, cnt(r), q * S, q * S + S, false, q});
     }
     if (world % 2 == 0) {
-        // the block pair (lo, hi = lo + P/2) is shared: lo takes every row of its shard against the first h bodies of hi,
-        // hi takes its rows behind h against all of lo
+        // the block pair (lo, hi = lo + P/2) is shared half and half: lo takes every row of its shard against the first h
+        // bodies of hi; hi takes its bodies from h on against all of lo.  h need not be a row boundary: hi's first row
+        // is then a partial ("virtual") row [h, next boundary), and the part of lo's partial row in hi's PJ that nobody
+        // writes stays zero (PJ buffers are zero-filled once).
         const int q = (p + world / 2) % world;
-        const int h = (R / 2) * SB;
+        const int h = (S / 2) / SUB * SUB;
         if (p < q) {
             if (h > 0)
-                for (int r = 0; r < R; r++) phases[1].push_back({r, q * S, q * S + h, false, q});
+                for (int r = 0; r < R; r++) phases[1].push_back({r * SB, cnt(r), q * S, q * S + h, false, q});
         } else {
-            for (int r = R / 2; r < R; r++) phases[1].push_back({r, q * S, q * S + S, false, q});
+            int i0 = h;
+            while (i0 < S) {
+                const int i1 = std::min(S, (i0 / SB + 1) * SB);
+                phases[1].push_back({i0, i1 - i0, q * S, q * S + S, false, q});
+                i0 = i1;
+            }
         }
     }
 }
@@ -82,15 +97,26 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
     std::vector<std::vector<Span>> phases;
     spans_of_rank(n, world, rank, phases);
     std::vector<std::vector<Seg>> per_block(blocks);
+    std::vector<double> got(blocks, 0.0);  // cost given to each block so far
+    double ideal_before = 0;               // what an exact split of the earlier phases would have given it
     for (const auto& spans : phases) {
         // cost of one SUB-wide unit of a span = bodies of the row x weight (one-sided: 16 instr per ordered pair, no
         // rotation, against 20 per unordered pair)
-        auto row_count = [&](int r) { return std::min(S, (r + 1) * SB) - r * SB; };
-        auto unit_cost = [&](const Span& s) { return row_count(s.row) * (s.onesided ? 0.8 : 1.0); };
+        auto unit_cost = [&](const Span& s) { return s.icount * (s.onesided ? 0.8 : 1.0); };
         double total = 0;
         for (const auto& s : spans) total += unit_cost(s) * ((s.j1 - s.j0 + SUB - 1) / SUB);
         if (total <= 0) continue;
-        const double per = total / blocks;
+        // block k's share of this phase = an equal part, corrected by what the rounding of the earlier phases gave it
+        // too much or too little; bound[k] = end of its window in cumulative cost
+        std::vector<double> bound(blocks);
+        {
+            double acc = 0;
+            for (int b = 0; b < blocks; b++) {
+                acc += std::max(0.0, total / blocks + (ideal_before - got[b]));
+                bound[b] = acc;
+            }
+            for (int b = 0; b < blocks; b++) bound[b] *= total / acc;  // the corrections sum to ~0; keep the windows exact
+        }
         double cum = 0;
         int k = 0;
         for (const auto& s : spans) {
@@ -103,7 +129,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
                     k = blocks - 1;
                     take = units - u0;
                 } else {
-                    const double room = per * (k + 1) - cum;
+                    const double room = bound[k] - cum;
                     take = (int)(room / w + 0.5);
                     if (take > units - u0) take = units - u0;
                     if (take <= 0) {
@@ -112,13 +138,13 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
                     }
                 }
                 Seg g{};
-                g.row_body0 = base + s.row * SB;
-                g.row_count = row_count(s.row);
+                g.row_body0 = base + s.i0;
+                g.row_count = s.icount;
                 g.j0 = s.j0 + u0 * SUB;
                 g.j1 = std::min(s.j1, s.j0 + (u0 + take) * SUB);
                 g.flags = s.onesided ? SEG_ONESIDED : 0;
                 g.pi_slot = -1;
-                g.pj_row = rank * P.rows_local + s.row;
+                g.pj_row = rank * P.rows_local + s.i0 / SB;  // a virtual row takes the number of the aligned row around it
                 g.src_rank = s.src;
                 per_block[k].push_back(g);
                 if (s.onesided)
@@ -126,30 +152,32 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
                 else
                     P.sym_pairs += (long long)g.row_count * (g.j1 - g.j0);
                 cum += take * w;
+                got[k] += take * w;
                 u0 += take;
-                if (k < blocks - 1 && cum >= per * (k + 1) - 0.5 * w) k++;
+                if (k < blocks - 1 && cum >= bound[k] - 0.5 * w) k++;
             }
         }
+        ideal_before += total / blocks;
     }
     // merge adjacent pieces of one span, mark row runs, number the PI slots row by row
     struct Flush {
         int row, block, idx;
     };
     std::vector<Flush> flushes;
+    auto same_row = [](const Seg& a, const Seg& b) { return a.row_body0 == b.row_body0 && a.row_count == b.row_count; };
     for (int b = 0; b < blocks; b++) {
         auto& v = per_block[b];
         std::vector<Seg> m;
         for (const Seg& g : v) {
-            if (!m.empty() && m.back().row_body0 == g.row_body0 && m.back().flags == g.flags && m.back().j1 == g.j0 &&
-                m.back().src_rank == g.src_rank)
+            if (!m.empty() && same_row(m.back(), g) && m.back().flags == g.flags && m.back().j1 == g.j0 && m.back().src_rank == g.src_rank)
                 m.back().j1 = g.j1;
             else
                 m.push_back(g);
         }
         v.swap(m);
         for (size_t i = 0; i < v.size(); i++) {
-            if (i == 0 || v[i - 1].row_body0 != v[i].row_body0) v[i].flags |= SEG_LOAD;
-            if (i + 1 == v.size() || v[i + 1].row_body0 != v[i].row_body0) {
+            if (i == 0 || !same_row(v[i - 1], v[i])) v[i].flags |= SEG_LOAD;
+            if (i + 1 == v.size() || !same_row(v[i + 1], v[i])) {
                 v[i].flags |= SEG_FLUSH;
                 flushes.push_back({(v[i].row_body0 - base) / SB, b, (int)i});
             }
@@ -158,9 +186,13 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
     std::stable_sort(flushes.begin(), flushes.end(), [](const Flush& a, const Flush& b) { return a.row < b.row; });
     P.pi_ptr.assign(P.rows_local + 1, 0);
     for (size_t s = 0; s < flushes.size(); s++) {
-        per_block[flushes[s].block][flushes[s].idx].pi_slot = (int)s;
+        Seg& g = per_block[flushes[s].block][flushes[s].idx];
+        g.pi_slot = (int)s;
         P.pi_ptr[flushes[s].row + 1]++;
+        // per slot: {slot, first local body, bodies}: a virtual row covers only part of the aligned row it lies in
         P.pi_list.push_back((int)s);
+        P.pi_list.push_back(g.row_body0 - base);
+        P.pi_list.push_back(g.row_count);
     }
     for (int r = 0; r < P.rows_local; r++) P.pi_ptr[r + 1] += P.pi_ptr[r];
     P.pi_slots = (int)flushes.size();
@@ -169,7 +201,8 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
         P.block_seg_begin[b + 1] = P.block_seg_begin[b] + (int)per_block[b].size();
         P.segs.insert(P.segs.end(), per_block[b].begin(), per_block[b].end());
     }
-    // which PJ rows hold contributions to the bodies of local row c: every rank's symmetric spans that cover it
+    // which PJ rows hold contributions to the bodies of local row c: every rank's symmetric spans that touch it (the
+    // part of such a PJ row that nobody writes stays zero)
     std::vector<std::vector<int>> contrib(P.rows_local);
     for (int p = 0; p < world; p++) {
         std::vector<std::vector<Span>> ph;
@@ -179,16 +212,14 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
                 if (s.onesided || s.src != rank) continue;
                 for (int c = 0; c < P.rows_local; c++) {
                     const int c0 = base + c * SB, c1 = base + std::min(S, (c + 1) * SB);
-                    if (s.j0 <= c0 && s.j1 >= c1)
-                        contrib[c].push_back(p * P.rows_local + s.row);
-                    else if (s.j0 < c1 && s.j1 > c0)
-                        return NB_ERR_UNSUPPORTED;  // a span must cover whole rows of the owner (planner invariant)
+                    if (s.j0 < c1 && s.j1 > c0) contrib[c].push_back(p * P.rows_local + s.i0 / SB);
                 }
             }
     }
     P.pj_ptr.assign(P.rows_local + 1, 0);
     for (int c = 0; c < P.rows_local; c++) {
         std::sort(contrib[c].begin(), contrib[c].end());
+        contrib[c].erase(std::unique(contrib[c].begin(), contrib[c].end()), contrib[c].end());
         P.pj_ptr[c + 1] = P.pj_ptr[c] + (int)contrib[c].size();
         P.pj_list.insert(P.pj_list.end(), contrib[c].begin(), contrib[c].end());
     }
@@ -199,6 +230,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
 namespace {
 
 constexpr int NT = 32 * WARPS;  // threads per block
+constexpr int ROT_UNROLL = NB_SYM_UNROLL;
 constexpr int TILE_BYTES = TJ * 32;
 constexpr int STG_DOUBLES = WARPS * 3 * TJ;  // one staging buffer
 constexpr size_t SMEM_BYTES = (size_t)STAGES * TILE_BYTES + 2 * (size_t)STG_DOUBLES * sizeof(double);
@@ -274,14 +306,18 @@ __device__ __forceinline__ void pair_sym(double xi, double yi, double zi, double
     aix = fma(ci, dx, aix);
     aiy = fma(ci, dy, aiy);
     aiz = fma(ci, dz, aiz);
+#if NB_SYM_EXP != 2  // timing experiment 2: without the a_j side (wrong results)
     ajx = fma(-cj, dx, ajx);
     ajy = fma(-cj, dy, ajy);
     ajz = fma(-cj, dz, ajz);
+#else
+    ajx += cj;
+#endif
 }
 
 __device__ __forceinline__ double rot(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-__global__ void __launch_bounds__(NT, 2) sym_accel_kernel(AccelArgs A, Peers peers) {
+__global__ void __launch_bounds__(NT, MIN_BLOCKS) sym_accel_kernel(AccelArgs A, Peers peers) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double4* tile = reinterpret_cast<double4*>(smem_raw);                         // [STAGES][TJ]
     double* stg = reinterpret_cast<double*>(smem_raw + STAGES * TILE_BYTES);      // [2][WARPS][3][TJ]
@@ -375,14 +411,18 @@ __global__ void __launch_bounds__(NT, 2) sym_accel_kernel(AccelArgs A, Peers pee
                     const double4 b = tj[min(jl, cnt - 1)];
                     double jx = b.x, jy = b.y, jz = b.z, jg = jl < cnt ? b.w : 0.0;
                     double ajx = 0.0, ajy = 0.0, ajz = 0.0;
-#pragma unroll 2
+#pragma unroll ROT_UNROLL
                     for (int r = 0; r < 32; r++) {
+                        // The j body moves on to the next lane with what it has collected; after 32 moves it is home
+                        // again.  Its position does not depend on this rotation's arithmetic: fetch it first.
+                        const double nx = rot(jx, src_lane), ny = rot(jy, src_lane), nz = rot(jz, src_lane), ng = rot(jg, src_lane);
 #pragma unroll
                         for (int k = 0; k < I_PER_LANE; k++)
                             pair_sym(xi[k], yi[k], zi[k], gi[k], jx, jy, jz, jg, ax[k], ay[k], az[k], ajx, ajy, ajz);
-                        // the j body moves on to the next lane with what it has collected; after 32 moves it is home again
-                        jx = rot(jx, src_lane), jy = rot(jy, src_lane), jz = rot(jz, src_lane), jg = rot(jg, src_lane);
+#if NB_SYM_EXP != 1  // timing experiment 1: accumulators stay (wrong results)
                         ajx = rot(ajx, src_lane), ajy = rot(ajy, src_lane), ajz = rot(ajz, src_lane);
+#endif
+                        jx = nx, jy = ny, jz = nz, jg = ng;
                     }
                     if (jl < cnt) my_stg[jl] = ajx, my_stg[TJ + jl] = ajy, my_stg[2 * TJ + jl] = ajz;
                 }
@@ -453,11 +493,15 @@ __global__ void __launch_bounds__(128) sym_integrate_kernel(IntegrateArgs A, Pee
     }
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il < A.shard) {
-        const int row = il / SB, off = il - row * SB;
+        const int row = il / SB;
         double a[3] = {0.0, 0.0, 0.0};
         for (int s = A.pi_ptr[row]; s < A.pi_ptr[row + 1]; s++) {
-            const double* p = A.pi + (size_t)A.pi_list[s] * 3 * SB + off;
-            a[0] += p[0], a[1] += p[SB], a[2] += p[2 * SB];
+            // {slot, first local body, bodies} of a row run that covers (part of) this aligned row
+            const int idx = il - A.pi_list[3 * s + 1];
+            if (idx >= 0 && idx < A.pi_list[3 * s + 2]) {
+                const double* p = A.pi + (size_t)A.pi_list[3 * s] * 3 * SB + idx;
+                a[0] += p[0], a[1] += p[SB], a[2] += p[2 * SB];
+            }
         }
         const int e = A.pj_ptr[row + 1];
 #pragma unroll 4
@@ -482,6 +526,32 @@ __global__ void __launch_bounds__(128) sym_integrate_kernel(IntegrateArgs A, Pee
         if (threadIdx.x < peers.world)
             red_release_sys(peers.counters[threadIdx.x] + (0 * 2 + A.parity) * MAX_PEERS + peers.my_rank);
     }
+}
+
+// run_step with HOST buffers (bench e2e): the caller's positions of this rank's bodies (planar, just copied host ->
+// device) become pos4 records in EVERY rank's current buffer, signalled like the integrate kernel's stores
+__global__ void __launch_bounds__(128) sym_publish_kernel(const double* __restrict__ q_own, const double* __restrict__ m0,
+                                                          const unsigned char* __restrict__ is_device, int shard, int i_begin,
+                                                          double fst, int parity, Peers peers) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il < shard) {
+        const int i = i_begin + il;
+        const double4 rec = make_double4(q_own[il], q_own[il + shard], q_own[il + 2 * shard], gm_eff(m0[i], is_device[i] != 0, fst));
+        for (int pr = 0; pr < peers.world; pr++) peers.pos4_next[pr][i] = rec;
+    }
+    if (peers.world > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < peers.world)
+            red_release_sys(peers.counters[threadIdx.x] + (0 * 2 + parity) * MAX_PEERS + peers.my_rank);
+    }
+}
+
+__global__ void sym_unpack_rows_kernel(const double4* __restrict__ pos4, int shard, int i_begin, double* __restrict__ q_own) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= shard) return;
+    const double4 p = pos4[i_begin + il];
+    q_own[il] = p.x, q_own[il + shard] = p.y, q_own[il + 2 * shard] = p.z;
 }
 
 // stream-ordered wait until every rank's rows of the last step have arrived (before the host reads the buffer)
@@ -510,6 +580,7 @@ struct nb_sym {
     int off_pi_list = 0, off_pj_ptr = 0, off_pj_list = 0;
     double* d_pi = nullptr;
     long long steps_done[2] = {0, 0};  // steps executed per parity
+    long long pos_pubs[2] = {0, 0};    // publications of this rank's rows per parity (integrate kernels + nb_sym_publish_rows)
     int first_step = -1, last_step = -1, accel_step = -1;
 };
 
@@ -562,6 +633,7 @@ int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, i
     return NB_OK;
 }
 
+int nb_sym_row_size(void) { return SB; }
 int nb_sym_rows(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : (n / world + SB - 1) / SB; }
 
 int nb_sym_create(int n, int world, int rank, nb_sym** out) {
@@ -641,7 +713,7 @@ int nb_sym_wait_positions(nb_sym* h, const unsigned long long* my_counters, int*
     if (h->plan.world == 1 || h->last_step < 0) return NB_OK;
     const int par = h->last_step & 1;
     sym_wait_kernel<<<1, h->plan.world, 0, (cudaStream_t)stream>>>(my_counters + (0 * 2 + par) * MAX_PEERS,
-                                                                  (unsigned long long)h->integrate_blocks * h->steps_done[par],
+                                                                  (unsigned long long)h->integrate_blocks * h->pos_pubs[par],
                                                                   status_dev);
     count_launch();
     NB_CUDA(cudaGetLastError());
@@ -673,7 +745,7 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur, d
     A.segs = h->d_segs, A.block_seg_begin = h->d_bsb, A.pi = h->d_pi, A.shard = P.shard;
     A.parity_read = (step - 1) & 1;
     // rows of step-1 were published by the integrate kernels of step-1 (none before the first step: packed locally)
-    A.pos_target = (P.world > 1 && h->last_step >= 0) ? (unsigned long long)h->integrate_blocks * h->steps_done[(step - 1) & 1] : 0;
+    A.pos_target = P.world > 1 ? (unsigned long long)h->integrate_blocks * h->pos_pubs[(step - 1) & 1] : 0;
     A.parity_acc = step & 1;
     A.status = status_dev;
     if (phases & 1) {
@@ -708,8 +780,42 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur, d
     count_launch();
     NB_CUDA(cudaGetLastError());
     h->steps_done[step & 1]++;
+    h->pos_pubs[step & 1]++;
     if (h->first_step < 0) h->first_step = step;
     h->last_step = step;
+    return NB_OK;
+}
+
+int nb_sym_publish_rows(nb_sym* h, int step_next, const double* q_own_planar_dev, double* const* peer_pos4_cur,
+                        unsigned long long* const* peer_counters, const double* m0_dev, const unsigned char* is_device_dev,
+                        void* stream) {
+    if (!h || step_next < 1 || !q_own_planar_dev || !peer_pos4_cur || !m0_dev || !is_device_dev) return NB_ERR_ARG;
+    const Plan& P = h->plan;
+    if (P.world > 1 && !peer_counters) return NB_ERR_ARG;
+    if (h->last_step >= 0 && step_next != h->last_step + 1) return NB_ERR_ARG;
+    Peers peers{};
+    peers.world = P.world, peers.my_rank = P.rank;
+    for (int p = 0; p < P.world; p++) {
+        if (!peer_pos4_cur[p] || (P.world > 1 && !peer_counters[p])) return NB_ERR_ARG;
+        peers.pos4_next[p] = (double4*)peer_pos4_cur[p];  // "next" = the buffer the coming step reads
+        peers.counters[p] = P.world > 1 ? peer_counters[p] : nullptr;
+    }
+    const int par = (step_next - 1) & 1;  // the parity the coming step's acceleration kernel waits on
+    sym_publish_kernel<<<h->integrate_blocks, 128, 0, (cudaStream_t)stream>>>(q_own_planar_dev, m0_dev, is_device_dev, P.shard,
+                                                                            P.rank * P.shard, fst_value(step_next), par, peers);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
+    h->pos_pubs[par]++;
+    return NB_OK;
+}
+
+int nb_sym_unpack_rows(nb_sym* h, const double* pos4_dev, double* q_own_planar_dev, void* stream) {
+    if (!h || !pos4_dev || !q_own_planar_dev) return NB_ERR_ARG;
+    const Plan& P = h->plan;
+    sym_unpack_rows_kernel<<<(P.shard + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const double4*)pos4_dev, P.shard,
+                                                                                  P.rank * P.shard, q_own_planar_dev);
+    count_launch();
+    NB_CUDA(cudaGetLastError());
     return NB_OK;
 }
 
@@ -741,6 +847,7 @@ int nb_sym_run_steps_host(int gpu, int n, double* q, double* v, const double* m,
     chk(cudaMalloc(&pos[0], 4 * (size_t)n * sizeof(double)), "cudaMalloc pos4");
     chk(cudaMalloc(&pos[1], 4 * (size_t)n * sizeof(double)), "cudaMalloc pos4");
     chk(cudaMalloc(&pj, (size_t)nb_sym_pj_bytes(h)), "cudaMalloc PJ");
+    if (rc == NB_OK) chk(cudaMemsetAsync(pj, 0, (size_t)nb_sym_pj_bytes(h), st), "memset PJ");
     if (rc == NB_OK) {
         chk(cudaMemcpyAsync(dq, q, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D q");
         chk(cudaMemcpyAsync(dv, v, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st), "H2D v");

@@ -7,11 +7,28 @@
 namespace nb {
 namespace sym {
 
-constexpr int I_PER_LANE = 4;            // i-bodies per lane
-constexpr int WARP_I = 32 * I_PER_LANE;  // i-bodies per warp (128)
-constexpr int WARPS = 8;                 // warps per block
-constexpr int SB = WARPS * WARP_I;       // bodies per row (superblock) = i-bodies per block (1024)
-constexpr int TJ = 128;                  // j bodies per shared-memory tile (4 KiB)
+// tuning knobs (A/B builds: -DNB_SYM_I=.. -DNB_SYM_WARPS=.. -DNB_SYM_MIN_BLOCKS=.. -DNB_SYM_TJ=..).  Measured on B200 at
+// n = 65536 (profiles/r02_sym_variants.md): 6 i-bodies per lane, 8 warps, ONE block per SM (254 registers: the six pair
+// chains of a rotation interleave instruction by instruction) 2.93 ms/step; 4 per lane at 128 registers, 16 warps/SM
+// (chains serialised by the register budget, 8-cycle dependent stalls) 3.28 ms; 12 warps x 168 registers 3.12 ms.
+#ifndef NB_SYM_I
+#define NB_SYM_I 6
+#endif
+#ifndef NB_SYM_WARPS
+#define NB_SYM_WARPS 8
+#endif
+#ifndef NB_SYM_MIN_BLOCKS
+#define NB_SYM_MIN_BLOCKS 1
+#endif
+#ifndef NB_SYM_TJ
+#define NB_SYM_TJ 128
+#endif
+constexpr int I_PER_LANE = NB_SYM_I;     // i-bodies per lane
+constexpr int WARP_I = 32 * I_PER_LANE;  // i-bodies per warp
+constexpr int WARPS = NB_SYM_WARPS;      // warps per block
+constexpr int MIN_BLOCKS = NB_SYM_MIN_BLOCKS;  // resident blocks per SM the register budget is set for
+constexpr int SB = WARPS * WARP_I;       // bodies per row (superblock) = i-bodies per block
+constexpr int TJ = NB_SYM_TJ;            // j bodies per shared-memory tile
 constexpr int STAGES = 3;                // TMA ring depth
 constexpr int SUB = 32;                  // scheduling granularity along j (one warp rotation group)
 constexpr int MAX_PEERS = 16;

@@ -329,6 +329,36 @@ class SymShardedSystem:
         for _ in range(steps):
             self.step_phase(3)
 
+    def pairs_per_step(self):
+        """Ordered pair interactions one step of THIS rank covers (2 x unordered symmetric pairs + the one-sided rows,
+        self pairs included)."""
+        return int(self.L.nb_sym_pairs(self.h, None, None))
+
+    def step_host(self, q_own_host, v_own_host):
+        """The run_step operator with HOST buffers (nbody.cc:51-54 signature, sharded): q_own_host / v_own_host are
+        pinned planar [3, n/world] tensors with THIS rank's positions and velocities (in: before the step, out: after).
+        Every call copies them host -> device, publishes the rows to every rank (peer stores), runs the step's two
+        kernels, extracts the new rows and copies them device -> host.  Returns (h2d bytes, d2h bytes)."""
+        from . import _check
+
+        C, L, torch = self.C, self.L, self.torch
+        if not hasattr(self, "_q_own"):
+            self._q_own = torch.empty(3 * self.i_count, dtype=torch.float64, device=self.device)
+        st = torch.cuda.current_stream().cuda_stream
+        self._q_own.copy_(q_own_host.view(-1), non_blocking=True)
+        self.vel.copy_(v_own_host, non_blocking=True)
+        _check(L.nb_sym_publish_rows(self.h, self.step + 1, C.c_void_p(self._q_own.data_ptr()), self.peer_pos[self.cur],
+                                     self.peer_ctr, C.c_void_p(self.m0.data_ptr()), C.c_void_p(self.isdev.data_ptr()),
+                                     C.c_void_p(st)))
+        self.step_phase(3)
+        # the rank's own rows of the new buffer were written by its own integrate kernel: stream order suffices
+        _check(L.nb_sym_unpack_rows(self.h, C.c_void_p(self.own[self.cur]), C.c_void_p(self._q_own.data_ptr()), C.c_void_p(st)))
+        q_own_host.view(-1).copy_(self._q_own, non_blocking=True)
+        v_own_host.copy_(self.vel, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nbytes = (q_own_host.numel() + v_own_host.numel()) * 8
+        return nbytes, nbytes
+
     def positions(self):
         """Planar q[3n] of all bodies (host numpy); waits for the last step's rows of every rank."""
         from . import _check

@@ -93,6 +93,20 @@ def test_io_errors_are_codes_not_exceptions_across_the_abi(nb, tmp_path):
     assert nb.lib().nb_write_output(b"/nonexistent/dir/x.out", 1.0, 1, 1, 1.0) == nb.NB_ERR_IO
 
 
+def test_read_input_rejects_out_of_range_planet_or_asteroid(nb, tmp_path):
+    """nbody.cc:118-120 indexes its arrays with the header's planet / asteroid unchecked; here a bad header is an I/O error."""
+    body = "0 0 0 0 0 0 1e20 star\n" * 3
+    for hdr in ("3 3 1", "3 0 -1", "3 7 7"):
+        p = tmp_path / "bad.in"
+        p.write_text(hdr + "\n" + body)
+        with pytest.raises(nb.NbodyError) as e:
+            nb.read_input(str(p))
+        assert e.value.code == nb.NB_ERR_IO
+    p = tmp_path / "ok.in"
+    p.write_text("3 2 1\n" + body)
+    assert nb.read_input(str(p)).planet == 2
+
+
 def test_argument_validation(nb):
     L = nb.lib()
     q = np.zeros(3)

@@ -9,7 +9,7 @@ import subprocess
 
 import numpy as np
 import pytest
-from conftest import CASES, GOLDEN, case_path, golden_lines
+from conftest import ROOT, CASES, GOLDEN, case_path, golden_lines
 
 pytestmark = pytest.mark.gpu
 MIN_DIST_RTOL = 1e-6  # tolerance the north star states for output line 1
@@ -281,6 +281,43 @@ def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
         assert o["argmin"] == k["argmin_step"]
         assert o["reach"] == [d["reach_step"] for d in k["devices"]]
         assert o["q3"] == [d["q3_hit_step"] for d in k["devices"]]
+
+
+def test_grid_kernel_large_then_small_then_large_in_one_process(nb):
+    """The dynamic shared-memory limit is an attribute of the kernel function: b1024 (160 KB), then b512 (80 KB), then
+    b1024 again in ONE process must not launch against a lowered limit (round-1 advisor finding, nb_grid.cu)."""
+    big, small = nb.read_input(case_path("b1024")), nb.read_input(case_path("b512"))
+    ref = {}
+    for name, s in (("b1024", big), ("b512", small), ("b1024", big), ("b512", small)):
+        t = nb.Trajectory(s, nb.KIND_Q1)
+        ev = t.run(3000)
+        q = t.state()[0]
+        t.close()
+        if name in ref:
+            assert np.array_equal(ref[name], q)
+        ref[name] = q
+        assert ev.steps_done == 3000
+
+
+def test_grid_kernel_unavailable_falls_back_to_single_block(nb):
+    """When the grid kernel's clusters cannot be co-resident (MIG / MPS / a shared GPU) the launch returns
+    NB_ERR_UNSUPPORTED before anything ran and the trajectory takes the single-block kernel: same discrete answers.
+    Forced here with NB_GRID_FORCE_UNSUPPORTED=1 in a subprocess."""
+    import sys
+    code = ("import importlib, sys\n"
+            "sys.path.insert(0, %r)\n"
+            "nb = importlib.import_module('nthu_ipc_nbody-simulation_b200')\n"
+            "s = nb.read_input(%r)\n"
+            "a = nb.solve(s, gpus=[0], n_steps=4000)\n"
+            "print(a.argmin_step, '%%.16e' %% a.min_dist, a.hit_time_step)\n") % (ROOT, case_path("b200"))
+    outs = []
+    for env in (dict(os.environ), dict(os.environ, NB_GRID_FORCE_UNSUPPORTED="1", NB_VERBOSE="1")):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        outs.append(r.stdout.decode().strip().split("\n")[-1])
+        if "NB_GRID_FORCE_UNSUPPORTED" in env:
+            assert "single-block kernel instead" in r.stderr.decode()
+    assert outs[0] == outs[1]
 
 
 # ---- nbtool: generator / ensembles / state files from the command line (SURVEY 8f rank 4) -----------------------

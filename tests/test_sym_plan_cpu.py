@@ -13,8 +13,13 @@ import torch.multiprocessing as mp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SB = 1024
 F_ONESIDED, F_LOAD, F_FLUSH = 1, 2, 4
+
+
+@pytest.fixture(autouse=True)
+def _row_size(nb):
+    global SB
+    SB = nb.lib().nb_sym_row_size()
 
 
 def plans(nb, n, world, blocks):
@@ -147,6 +152,8 @@ def _worker(rank, world, port, n, blocks, ret):
     from importlib import import_module
 
     nb = import_module("nthu_ipc_nbody-simulation_b200")
+    global SB
+    SB = nb.lib().nb_sym_row_size()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         S = n // world
@@ -181,7 +188,9 @@ def _worker(rank, world, port, n, blocks, ret):
             lo, hi = c * SB, min(S, (c + 1) * SB)
             listed = list(pj_list[pj_ptr[c]:pj_ptr[c + 1]])
             for row in range(world * rows):
-                assert have[row, lo:hi].all() == (row in listed) and have[row, lo:hi].any() == (row in listed)
+                # a listed PJ row may be written only in part (the shared block pair is cut at shard/2, not at a row
+                # boundary): the rest stays zero, as in the zero-filled device buffer
+                assert have[row, lo:hi].any() == (row in listed)
             for row in listed:
                 a[lo:hi] += pj[row, lo:hi]
         parts = [None] * world
@@ -192,7 +201,7 @@ def _worker(rank, world, port, n, blocks, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,world,blocks", [(4096, 2, 5), (6144, 2, 8)])
+@pytest.mark.parametrize("n,world,blocks", [(4096, 2, 5), (6144, 2, 8), (10000, 2, 7)])
 def test_executed_plan_two_ranks_gloo(nb, n, world, blocks):
     port = 29600 + (os.getpid() % 300)
     with mp.Manager() as mgr:

@@ -138,14 +138,27 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 template <int NTHREADS>
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-// Record layout: one 32-byte sector {x, y, z, step tag}: the unit the L2 reads and writes.
-__device__ __forceinline__ double make_tag(int step) { return __longlong_as_double((long long)step); }
-__device__ __forceinline__ bool tag_is(double tg, int step) { return __double_as_longlong(tg) == (long long)step; }
+// Record layout: one 32-byte sector {x, y, z, tag}.  The tag is SELF-CHECKING: step XOR a fold of the bit patterns of
+// x, y and z, so a record is accepted only if all four words belong together.  The design relies on a naturally aligned
+// 32-byte access being one L2 sector transaction (see the header comment), which the PTX memory model does not promise
+// for vector or bulk accesses; with this tag a torn record - any mixture of words of two publications - fails the
+// check (up to a 2^-64 coincidence) and is polled again instead of being consumed.
+__device__ __forceinline__ unsigned long long fold3(double x, double y, double z) {
+    const unsigned long long a = (unsigned long long)__double_as_longlong(x), b = (unsigned long long)__double_as_longlong(y),
+                             c = (unsigned long long)__double_as_longlong(z);
+    return a ^ ((b << 21) | (b >> 43)) ^ ((c << 42) | (c >> 22));
+}
+__device__ __forceinline__ double make_tag(int step, double x, double y, double z) {
+    return __longlong_as_double((long long)((unsigned long long)(long long)step ^ fold3(x, y, z)));
+}
+__device__ __forceinline__ bool tag_ok(double tg, int step, double x, double y, double z) {
+    return (unsigned long long)__double_as_longlong(tg) == ((unsigned long long)(long long)step ^ fold3(x, y, z));
+}
 
 struct Shared {
     // stage = step parity.  full: the copies of all R records have landed (1 arrival = the producer's expect_tx, plus
     // the bytes); obs: the observer has judged the step (1 arrival).  Each completes once per two steps.
-    alignas(8) uint64_t full[MAX_T][2];
+    alignas(8) uint64_t full[MAX_T][2][MAX_CS];  // one per slice of the exchange (cluster rank), see below
     alignas(8) uint64_t obs[MAX_T][2];
     alignas(8) uint64_t trig[MAX_T][2];  // producer trigger: this block's sums of the step are complete (1 arrival)
     volatile int flags[MAX_T][2];   // FLAG_* of the step held by the stage, valid once obs completed
@@ -167,7 +180,7 @@ struct ObsState {  // per system, observer warp
 template <int MATH, int T, int NJ, bool PROFILE>
 __global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single) {
+                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single, int groups) {
     extern __shared__ __align__(128) double smem[];
     __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,7 +206,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             // a trajectory that stopped in an earlier launch never steps again
             sh.stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
             for (int b = 0; b < 2; b++) {
-                mbar_init(&sh.full[t][b], 1);
+                for (int sl = 0; sl < MAX_CS; sl++) mbar_init(&sh.full[t][b][sl], 1);
                 mbar_init(&sh.obs[t][b], 1);
                 mbar_init(&sh.trig[t][b], 1);
                 sh.flags[t][b] = 0;
@@ -220,11 +233,13 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 ga = gm_eff(d.m[r], dev, f1);
                 gb = dev ? 0.0 : ga;
             }
-            p0[4 * r] = x, p0[4 * r + 1] = y, p0[4 * r + 2] = z, p0[4 * r + 3] = make_tag(sb);
-            p1[4 * r] = 0.0, p1[4 * r + 1] = 0.0, p1[4 * r + 2] = 0.0, p1[4 * r + 3] = make_tag(-1);
+            p0[4 * r] = x, p0[4 * r + 1] = y, p0[4 * r + 2] = z, p0[4 * r + 3] = make_tag(sb, x, y, z);
+            p1[4 * r] = 0.0, p1[4 * r + 1] = 0.0, p1[4 * r + 2] = 0.0, p1[4 * r + 3] = make_tag(-1, 0.0, 0.0, 0.0);
             g0[r] = ga, g1[r] = gb;
         }
     }
+    // the stages were filled through the generic proxy; the TMA (async proxy) overwrites them from the next step on
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     cluster_sync_all();  // every block's mbarriers exist before anybody multicasts into them
 
@@ -233,24 +248,22 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         const long long t0 = clock64();
         do {
             ld_sector(grec + 4 * (size_t)r, x, y, z, tg);
+            if (sh.abort) break;
             if (clock64() - t0 > SPIN_LIMIT) {
                 sh.abort = 1;
                 atomicExch(status, 1);
                 break;
             }
-        } while (!tag_is(tg, st));
+        } while (!tag_ok(tg, st, x, y, z));
     };
-    // A record of step `st` for the observer: out of shared memory if its tag is current, else out of global memory.
-    // The compute warps patch stale shared-memory records coordinates first, tag last (patch_rec), so the tag is read first.
+    // A record of step `st` for the observer: out of shared memory if it passes the self-check, else out of global memory.
     auto load_rec = [&](const double* pos, const double* grec, int r, int st, double& x, double& y, double& z) {
+        // The compute warps patch stale shared-memory records word by word (patch_rec): a record caught half patched
+        // fails the self-check like any torn record and is fetched from global memory instead.
         const volatile double* vp = pos + 4 * r;
         double tg = vp[3];
-        if (tag_is(tg, st)) {
-            __threadfence_block();
-            x = vp[0], y = vp[1], z = vp[2];
-        } else {
-            poll_rec(grec, r, st, x, y, z, tg);
-        }
+        x = vp[0], y = vp[1], z = vp[2];
+        if (!tag_ok(tg, st, x, y, z)) poll_rec(grec, r, st, x, y, z, tg);
     };
     // fetch a stale record from global memory and patch shared memory: coordinates, fence, then the tag
     auto patch_rec = [&](double* pos, const double* grec, int r, int st) {
@@ -305,8 +318,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         continue;
                     }
                     const long long t1 = clock64();
-                    uint64_t* bar = &sh.full[t][st & 1];
-                    mbar_arrive_expect_tx(bar, (uint32_t)R * 32u);
+                    // slice s of the record array arrives from cluster rank s (its multicast) on mbarrier s of every block:
+                    // arm all of this block's slice barriers, then copy this rank's slice into everybody
+                    for (uint32_t sl = 0; sl < CS; sl++) mbar_arrive_expect_tx(&sh.full[t][st & 1][sl], slice * 32u);
+                    uint64_t* bar = &sh.full[t][st & 1][rank];
                     // Copy delay after the trigger: long enough for everybody's sectors of this step to be in the L2 when the
                     // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
                     // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
@@ -363,7 +378,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 ObsState& s = os[t];
                 if (!s.active) continue;
                 const int st = s.step, stage = st & 1;
-                if (st > s.step_begin && !wait_bar(&sh.full[t][stage], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u)) {
+                bool landed = true;
+                if (st > s.step_begin)
+                    for (uint32_t sl = 0; sl < cluster_nctarank() && landed; sl++)
+                        landed = wait_bar(&sh.full[t][stage][sl], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u);
+                if (!landed) {
                     s.active = false;
                     continue;
                 }
@@ -446,13 +465,24 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         const int bg = warp / NJ, part = warp % NJ;
         const int body0 = c * GB + bg * BPW;  // the warp's four bodies (records body0 .. body0+3)
         const int hsel = (lane >> 2) & 1;     // conflict-free LDS.128 pairs: these lanes read the second half first
-        // integrator threads (warp 0, lane < 24): body 8c + lane/3, component lane%3
-        const int ib = lane / 3, ik = lane - 3 * ib;
-        const int my_body = c * GB + ib;
-        const bool integ = warp == 0 && lane < 3 * GB;
+        // Every warp integrates ITS four bodies itself (lanes 0..11: body lane/3, component lane%3; the NJ warps of a body
+        // group do identical arithmetic on identical inputs), so the positions of the own bodies never wait for the
+        // exchange and no second block barrier is needed; the warp with part == 0 publishes.
+        const int wb = lane / 3, wk = lane - 3 * wb;
+        const int w_body = body0 + wb;
+        const bool winteg = lane < 3 * BPW;
+        // the exchange lands slice by slice (one slice per cluster rank, one mbarrier each): when a slice is a whole number
+        // of warp strides the pair loop starts on slice 0 while the others are still in flight
+        const int CSn = (int)cluster_nctarank();
+        const int slice = R / CSn;
+        // groups of spg slices are waited for, validated and consumed one after another (groups <= 0: one group = the
+        // un-pipelined exchange; the padded tail of the stage, zero mass, belongs to the single group only)
+        int G = groups > 0 && groups <= CSn && CSn % groups == 0 && ((slice * (CSn / groups)) % RQ) == 0 ? groups : 1;
+        const int spg = CSn / G;
+        const int gsize = G > 1 ? slice * spg : RS;
         int cstep[T], cbegin[T], cend[T];
         bool cact[T];
-        double iq[T], iv[T];
+        double wq[T], wv[T];
         long long pacc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
         unsigned long long n_stale = 0;
         auto tick = [&](int phase) {
@@ -468,9 +498,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             const TrajDesc& d = descs[t];
             cstep[t] = cbegin[t] = d.step_begin, cend[t] = d.step_end;
             cact[t] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
-            const bool mine = integ && my_body < n;
-            iq[t] = mine ? d.q[ik * n + my_body] : 0.0;
-            iv[t] = mine ? d.v[ik * n + my_body] : 0.0;
+            const bool mine = winteg && w_body < n;
+            wq[t] = mine ? d.q[wk * n + w_body] : 0.0;
+            wv[t] = mine ? d.v[wk * n + w_body] : 0.0;
             any |= cact[t];
         }
         long long g0 = 0, c0 = 0;
@@ -488,62 +518,67 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 if (PROFILE) pt = clock64();
                 const int st = cstep[t], stage = st & 1;
                 const bool last = st >= cend[t];
-                // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
-                if (!last && st > cbegin[t]) wait_bar(&sh.full[t][stage], (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u);
-                tick(0);
                 double* pos = s_pos(t, stage);
                 const double* cg = s_gm(t, stage);
                 const double* grec = g_rec(t, st);
+                const uint32_t fpar = (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u;
                 double ax[BPW], ay[BPW], az[BPW];
                 int flags = 0;
-                if (!last) {
-                    // (0) validate: every record of the stage must carry this step's tag (thread tid checks records
-                    //     tid + 256k; the tags of 32 consecutive records share 8 banks, so this pass is shared-memory bound: ~256 clk at
-                    //     n = 1024).  A stale record was copied
-                    //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
-                    //     memory and patch shared memory, each stale record by exactly one thread of the block.
-                    bool patched = false;
-                    double tgv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int r = tid + 256 * k;
-                        tgv[k] = r < R ? pos[4 * r + 3] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int r = tid + 256 * k;
-                        if (r < R && !tag_is(tgv[k], st)) {
-                            patch_rec(pos, grec, r, st);
-                            patched = true;
-                            n_stale++;
-                        }
-                    }
-                    // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
-                    if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    compute_bar<32 * NCW>();
-                }
-                tick(5);
                 for (int attempt = 0; attempt < 2; attempt++) {
 #pragma unroll
                     for (int i = 0; i < BPW; i++) ax[i] = ay[i] = az[i] = 0.0;
                     if (!last) {
-                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records
+                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records.  The own
+                        //     positions come out of the warp's integrator lanes, not out of the exchange.
                         double xi[BPW], yi[BPW], zi[BPW];
 #pragma unroll
                         for (int i = 0; i < BPW; i++) {
-                            const double* p = pos + 4 * (body0 + i);
-                            xi[i] = p[0], yi[i] = p[1], zi[i] = p[2];
+                            xi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i);
+                            yi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i + 1);
+                            zi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i + 2);
                         }
+                        for (int g = 0; g < G; g++) {
+                            // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
+                            if (st > cbegin[t])
+                                for (int sl = g * spg; sl < (g + 1) * spg; sl++) wait_bar(&sh.full[t][stage][sl], fpar);
+                            if (g == 0) tick(0);
+                            // (0) validate the group that has just landed, all 256 threads in parallel (thread tid checks records
+                            //     tid + 256k of the group): a record that was copied before its publication, or torn, fails the
+                            //     self-check - this is how the fast blocks wait for the slowest.  Poll that sector in global
+                            //     memory and patch shared memory, each stale record by exactly one thread of the block; the
+                            //     polls of a group overlap, so a late block costs everybody one L2 round trip, not one per record.
+                            bool patched = false;
+                            for (int i = tid; i < gsize; i += 32 * NCW) {
+                                const int r = g * gsize + i;
+                                if (r < R) {
+                                    const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
+                                    const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
+                                    const double2 lo = hsel ? B : A, hi = hsel ? A : B;
+                                    if (!tag_ok(hi.y, st, lo.x, lo.y, hi.x)) {
+                                        patch_rec(pos, grec, r, st);
+                                        patched = true;
+                                        n_stale++;
+                                    }
+                                }
+                            }
+                            // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
+                            if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            compute_bar<32 * NCW>();
+                            if (g == 0) tick(5);
 #pragma unroll 2
-                        for (int r = 32 * part + lane; r < RS; r += RQ) {
-                            // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
-                            const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
-                            const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
-                            const double jx = hsel ? B.x : A.x, jy = hsel ? B.y : A.y, jz = hsel ? A.x : B.x;
-                            const double jg = cg[r];
+                            for (int i = 32 * part + lane; i < gsize; i += RQ) {
+                                const int r = g * gsize + i;
+                                // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
+                                const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
+                                const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
+                                const double jx = hsel ? B.x : A.x, jy = hsel ? B.y : A.y, jz = hsel ? A.x : B.x;
+                                const double jg = cg[r];
 #pragma unroll
-                            for (int i = 0; i < BPW; i++) pair<MATH>(xi[i], yi[i], zi[i], jx, jy, jz, jg, ax[i], ay[i], az[i]);
+                                for (int b = 0; b < BPW; b++) pair<MATH>(xi[b], yi[b], zi[b], jx, jy, jz, jg, ax[b], ay[b], az[b]);
+                            }
                         }
+                    } else {
+                        tick(0);
                     }
                     tick(1);
                     // (2) the observer's verdict on the positions of step st
@@ -591,25 +626,26 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     }
                 }
                 tick(3);
-                compute_bar<32 * NCW>();
+                compute_bar<32 * NCW>();  // the only block barrier of a step: the j-parts meet
                 if (sh.abort) {  // an exchange wait timed out somewhere in this block
                     aborted = true;
                     break;
                 }
-                // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
-                //     tagged sector {x, y, z, step}, unfenced
-                if (warp == 0) {
-                    if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
-                    if (integ) {
-                        const double* p = &sh.part[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
-                        double a = p[0];
+                // (4) a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88) in every warp; the part-0 warp of a
+                //     body group publishes each body as one self-checking sector {x, y, z, tag}, unfenced
+                if (tid == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
+                if (winteg) {
+                    const double* p = &sh.part[pbuf][bg * NJ][3 * wb + wk];
+                    double a = p[0];
 #pragma unroll
-                        for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
-                        if (my_body < n) kick_drift(a, iv[t], iq[t]);
-                    }
-                    const double qy = __shfl_down_sync(0xffffffffu, iq[t], 1);
-                    const double qz = __shfl_down_sync(0xffffffffu, iq[t], 2);
-                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[t], qy, qz, make_tag(st + 1));
+                    for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
+                    if (w_body < n) kick_drift(a, wv[t], wq[t]);
+                }
+                {
+                    const double qy = __shfl_down_sync(0xffffffffu, wq[t], 1);
+                    const double qz = __shfl_down_sync(0xffffffffu, wq[t], 2);
+                    if (part == 0 && winteg && wk == 0)
+                        st_sector(g_rec(t, st + 1) + 4 * (size_t)w_body, wq[t], qy, qz, make_tag(st + 1, wq[t], qy, qz));
                 }
                 cstep[t] = st + 1;
                 pbuf ^= 1;
@@ -635,12 +671,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         }
         if (PROFILE && n_stale) atomicAdd((unsigned long long*)&prof[5], n_stale);
         // write back
-        if (integ && my_body < n) {
+        if (part == 0 && winteg && w_body < n) {
 #pragma unroll
             for (int t = 0; t < T; t++) {
                 const TrajDesc& d = descs[t];
-                d.q[ik * n + my_body] = iq[t];
-                d.v[ik * n + my_body] = iv[t];
+                d.q[wk * n + w_body] = wq[t];
+                d.v[wk * n + w_body] = wv[t];
             }
         }
     }
@@ -747,7 +783,14 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         }
     }
     const auto h0 = std::chrono::steady_clock::now();
-    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single));
+    // pipeline depth of the exchange: 1 = wait for all slices, then validate and compute (default); 2 / 4 = consume the
+    // slices group by group as they land.  Measured on B200, b1024 (profiles/r02_grid_pipeline.md): 3.80 / 4.49 / 4.87
+    // us per step at delay 900 - the blocks keep in step only through the data, and with a validate + barrier per group a
+    // block that polls in one group is late for the next, whose records the others then find stale (30 000 stale records
+    // per step against 5 000): the pipeline loses more in polls than it hides in copy time.
+    static const int groups_env = env_int("NB_GRID_GROUPS", 1);
+    int groups = groups_env;
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single, groups));
     count_launch();
     {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
@@ -766,7 +809,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         fprintf(stderr, "grid kernel %.3f ms by events | block entry spread %.1f us | first entry -> last block done %.3f ms | block done spread %.1f us\n",
                 kms, (h[9] - h[8]) * 1e-3, (h[11] - h[8]) * 1e-6, (h[11] - h[10]) * 1e-3);
         fprintf(stderr,
-                "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait copy %lld | validate %lld | pairs %lld | wait observer %lld | "
+                "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait first group %lld | validate first group %lld | pairs + later groups %lld | wait observer %lld | "
                 "butterfly %lld | barrier+integrate+publish %lld | stale records polled (all blocks) %lld | SM clock %lld MHz\n",
                 T, NJ, cs, delay_clk, h[0], h[6], h[1], h[2], h[3], h[4], h[5], h[7]);
     }

@@ -492,7 +492,10 @@ int nb_run_steps(int gpu, int math, int n, double* q, double* v, const double* m
 //     chunk before the arrival instead of at step 0 (a fork started before the arrival is bit-identical to a
 //     run from step 0).  The candidates are then tried in order of arrival step = order of cost, and the search
 //     stops at the first one that saves the planet (hw5.cu:491-492, 509-517): the others cost more.  Part 0 runs
-//     Q1 (in lock step with the chain when it is the only part), part 1 the chain; further parts stay idle.
+//     Q1 (in lock step with the chain when it is the only part), part 1 the chain.  Further parts (2 < GPUs <
+//     trajectories) SPECULATE: part 2 + s simulates, from step 0, the query-3 trajectory of the device that is s-th
+//     nearest to the planet at step 0 (the missile flies at a fixed speed, so that is the likely order of arrival);
+//     the chain leaves those devices out and nb_solve_combine picks the cheapest saviour among everything simulated.
 static const int NB_SOLVE_CHUNK = [] {
     const int v = getenv("NB_SOLVE_CHUNK") ? atoi(getenv("NB_SOLVE_CHUNK")) : 8192;
     return v < 1 ? 1 : v;  // 0 or negative would never advance the chain
@@ -523,9 +526,26 @@ int nb_solve_trajectory_count(const nb_system* sys, int* count) {
 }
 
 
-// CHAIN plan on one GPU (see above): slot 0 = Q1 (optional), last slot = Q2, then the Q3 candidates one after another
-static int solve_chain(const nb_system* sys, const std::vector<int>& devs, int gpu, bool with_q1, bool with_chain, int n_steps,
-                       int math, nb_events* evs, double* gpu_seconds, long long* pair_interactions) {
+// devices (indexes into devs) by distance to the planet at step 0, nearest first; ties by index
+static std::vector<int> speculation_order(const nb_system* sys, const std::vector<int>& devs) {
+    const int n = sys->n, P = sys->planet;
+    std::vector<std::pair<double, int>> d;
+    for (int k = 0; k < (int)devs.size(); k++) {
+        const int b = devs[k];
+        const double dx = sys->q[b] - sys->q[P], dy = sys->q[b + n] - sys->q[P + n], dz = sys->q[b + 2 * n] - sys->q[P + 2 * n];
+        d.emplace_back(dx * dx + dy * dy + dz * dz, k);
+    }
+    std::sort(d.begin(), d.end());
+    std::vector<int> order;
+    for (auto& e : d) order.push_back(e.second);
+    return order;
+}
+
+// CHAIN plan on one GPU (see above): slot 0 = Q1 (optional), last slot = Q2, then the Q3 candidates one after another;
+// devices flagged in `speculated` are simulated elsewhere and left out
+static int solve_chain(const nb_system* sys, const std::vector<int>& devs, const std::vector<char>& speculated, int gpu,
+                       bool with_q1, bool with_chain, int n_steps, int math, nb_events* evs, double* gpu_seconds,
+                       long long* pair_interactions) {
     const bool verbose = getenv("NB_VERBOSE") != nullptr;
     const int n = sys->n, dc = (int)devs.size();
     const size_t sbytes = 3 * (size_t)n * sizeof(double);
@@ -593,14 +613,15 @@ static int solve_chain(const nb_system* sys, const std::vector<int>& devs, int g
         }
         if (rc) return cleanup(rc);
         evs[1] = b.h_ev[sl];
-        for (int k = 0; k < dc; k++) {  // "not simulated" until tried
+        for (int k = 0; k < dc; k++) {  // "not simulated" until tried; a speculated device is another part's entry
             DeviceBatch::fresh_events(evs[2 + k]);
+            if (speculated[k]) evs[2 + k].steps_done = -2;
         }
         // ---- Q3: candidates by arrival step (= by cost, hw5.cu:575-585), first saviour wins (hw5.cu:491-492)
         if (evs[1].hit_step != -2) {
             std::vector<int> order;
             for (int k = 0; k < dc; k++)
-                if (snap_step[k] >= 0) order.push_back(k);
+                if (snap_step[k] >= 0 && !speculated[k]) order.push_back(k);
             std::stable_sort(order.begin(), order.end(),
                              [&](int a, int c2) { return evs[1].reach_step[a] < evs[1].reach_step[c2]; });
             for (int k : order) {
@@ -653,10 +674,19 @@ int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n
     }
     if (gpu_seconds) *gpu_seconds = 0;
     if (pair_interactions) *pair_interactions = 0;
-    if (solve_chain_plan(n_parts, 2 + (int)devs.size(), math_flags)) {
-        if (part > 1) return NB_OK;
-        return solve_chain(sys, devs, gpu, /*with_q1=*/part == 0, /*with_chain=*/n_parts == 1 || part == 1, n_steps, math, evs,
-                           gpu_seconds, pair_interactions);
+    const int T = 2 + (int)devs.size();
+    std::vector<int> mine;  // trajectories this part simulates from step 0 in one launch
+    if (solve_chain_plan(n_parts, T, math_flags)) {
+        std::vector<char> speculated(devs.size(), 0);
+        const std::vector<int> order = speculation_order(sys, devs);
+        for (int p = 2; p < n_parts && p - 2 < (int)order.size(); p++) speculated[order[p - 2]] = 1;
+        if (part <= 1)
+            return solve_chain(sys, devs, speculated, gpu, /*with_q1=*/part == 0, /*with_chain=*/n_parts == 1 || part == 1, n_steps,
+                               math, evs, gpu_seconds, pair_interactions);
+        if (part - 2 >= (int)order.size()) return NB_OK;
+        mine.push_back(2 + order[part - 2]);
+    } else {
+        for (int t = part; t < T; t += n_parts) mine.push_back(t);
     }
     const bool verbose = getenv("NB_VERBOSE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -665,9 +695,6 @@ int nb_solve_partial(const nb_system* sys, int gpu, int part, int n_parts, int n
     rc = nb::check_gpu(gpu);
     if (rc) return rc;
     const double s_driver = secs_since(t_a);
-    const int T = 2 + (int)devs.size();
-    std::vector<int> mine;
-    for (int t = part; t < T; t += n_parts) mine.push_back(t);
     if (gpu_seconds) *gpu_seconds = 0;
     if (pair_interactions) *pair_interactions = 0;
     if (mine.empty()) return NB_OK;
@@ -742,8 +769,7 @@ int nb_solve(const nb_system* sys, const int* gpus, int n_gpus, int n_steps, int
     if (!ans || n_gpus < 1 || n_steps < 0) return NB_ERR_ARG;
     auto t_begin = std::chrono::steady_clock::now();
     const int T = 2 + (int)devs.size();
-    int G = n_gpus < T ? n_gpus : T;
-    if (solve_chain_plan(G, T, math) && G > 2) G = 2;  // chain plan: Q1 on one GPU, Q2 -> Q3 on another
+    const int G = n_gpus < T ? n_gpus : T;  // chain plan with more than two GPUs: the spare ones speculate (see above)
     std::vector<int> gl(G);
     for (int g = 0; g < G; g++) {
         gl[g] = gpus ? gpus[g] : g;

@@ -283,6 +283,72 @@ def test_grid_kernel_forced_on_small_systems(nb, tmp_path):
         assert o["q3"] == [d["q3_hit_step"] for d in k["devices"]]
 
 
+@pytest.mark.parametrize("case", ["b80", "b90", "b200"])
+def test_scheduler_parts_between_two_and_trajectory_count(nb, case, kats):
+    """2 < GPUs < trajectories (hw5.cu:448-457, 575-588 generalised): part 0 = query 1, part 1 = query 2 -> the query-3
+    candidates it was left with, parts 2.. = speculative query-3 trajectories (from step 0) of the devices nearest to the
+    planet.  The parts run one after another on this GPU and are merged exactly as solve_distributed / nb_solve do."""
+    s = nb.read_input(case_path(case))
+    g = golden_lines(case)
+    T = 2 + len(s.devices)
+    for n_parts in range(3, T):
+        merged = None
+        spare_entries = 0
+        for part in range(n_parts):
+            evs, secs, pairs = nb.solve_partial(s, 0, part, n_parts)
+            if merged is None:
+                merged = (nb.NbEvents * T)()
+                for t in range(T):
+                    merged[t].steps_done = -2
+            for t in range(T):
+                if evs[t].steps_done != -2:
+                    assert merged[t].steps_done == -2, "a trajectory belongs to one part"
+                    merged[t] = evs[t]
+                    if part >= 2:
+                        spare_entries += 1
+                        assert t >= 2 and evs[t].steps_done >= 0
+        assert spare_entries == n_parts - 2, "every spare part simulated one query-3 trajectory"
+        ans = nb.solve_combine(s, merged)
+        assert (ans.hit_time_step, ans.gravity_device_id, ans.missile_cost) == (
+            g["hit_time_step"], g["gravity_device_id"], g["missile_cost"]), n_parts
+        assert abs(ans.min_dist - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+        for k, d in enumerate(kats[case]["devices"]):  # whatever was simulated agrees with the oracle's per-device outcome
+            if ans.q3_hit_step[k] != -3:
+                assert ans.q3_hit_step[k] == d["q3_hit_step"]
+
+
+def test_grid_exchange_knobs_never_change_results_full_length(nb):
+    """The fence-free exchange of the grid kernel (self-checking 32-byte records, TMA multicast, poll-and-patch) is
+    timing-dependent by design; its RESULTS must not be.  b1024 and b512, all 200 000 steps, with clusters of 1 / 2 / 4,
+    the copy issued with no delay at all (every record stale at first: all go through the poll-and-patch path), one
+    or two systems per launch: final q and v bit-identical, same events."""
+    import sys
+    code = ("import importlib, hashlib, json, sys\n"
+            "sys.path.insert(0, %r)\n"
+            "nb = importlib.import_module('nthu_ipc_nbody-simulation_b200')\n"
+            "out = {}\n"
+            "for case in ('b1024', 'b512'):\n"
+            "    s = nb.read_input(%r + '/' + case + '.in')\n"
+            "    a = nb.Trajectory(s, nb.KIND_Q1)\n"
+            "    ev = a.run(nb.N_STEPS)\n"
+            "    q, v, m, step = a.state()\n"
+            "    out[case] = [hashlib.sha256(q.tobytes() + v.tobytes()).hexdigest(), ev.argmin_step, repr(ev.min_d2), step]\n"
+            "    ans = nb.solve(s, gpus=[0])\n"
+            "    out[case] += [nb.format_output(ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost)]\n"
+            "print(json.dumps(out))\n") % (ROOT, os.path.join(GOLDEN, "testcases"))
+    results = {}
+    for name, knobs in (("default", {}), ("cs1", dict(NB_GRID_CS="1")), ("cs2_t1", dict(NB_GRID_CS="2", NB_GRID_T="1")),
+                        ("cs4_delay0", dict(NB_GRID_CS="4", NB_GRID_DELAY="0")), ("cs2_delay0_t2", dict(NB_GRID_CS="2", NB_GRID_DELAY="0", NB_GRID_T="2")),
+                        ("delay5000", dict(NB_GRID_DELAY="5000"))):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, **knobs), timeout=900)
+        assert r.returncode == 0, (name, r.stderr.decode()[-2000:])
+        results[name] = json.loads(r.stdout.decode().strip().split("\n")[-1])
+    for name, res in results.items():
+        assert res == results["default"], name
+    for case in ("b1024", "b512"):
+        assert results["default"][case][4] == golden_lines(case)["text"]
+
+
 def test_grid_kernel_large_then_small_then_large_in_one_process(nb):
     """The dynamic shared-memory limit is an attribute of the kernel function: b1024 (160 KB), then b512 (80 KB), then
     b1024 again in ONE process must not launch against a lowered limit (round-1 advisor finding, nb_grid.cu)."""

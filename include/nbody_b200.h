@@ -99,6 +99,10 @@ const char* nb_last_error_detail(void); /* thread-local text of the last NB_ERR_
 int nb_device_count(int* count);        /* NB_ERR_NO_GPU when there is none          */
 /* launches of this library's kernels made by the calling process so far (for bench accounting) */
 long long nb_kernel_launches(void);
+/* Records of the grid kernel's fence-free exchange that passed the step check but failed the full self-check (a torn
+ * 32-byte sector) and were fetched again, in this process so far.  Expected: 0 (the hardware reads and writes whole
+ * sectors); a non-zero count is harmless for the results and worth reporting. */
+long long nb_grid_torn_records(void);
 
 /* ---- the step operator -------------------------------------------------------------------
  * Replaces run_step(step, n, qx,qy,qz, vx,vy,vz, m, type) (nbody.cc:51-89) and the kernel pair

@@ -66,7 +66,7 @@ class NbAnswer(C.Structure):
 
 # every symbol include/nbody_b200.h declares (tests/test_abi.py checks the two lists agree)
 ABI_SYMBOLS = [
-    "nb_version", "nb_strerror", "nb_last_error_detail", "nb_device_count", "nb_kernel_launches",
+    "nb_version", "nb_strerror", "nb_last_error_detail", "nb_device_count", "nb_kernel_launches", "nb_grid_torn_records",
     "nb_run_steps", "nb_traj_create", "nb_traj_run", "nb_traj_state", "nb_traj_fork", "nb_traj_fork_on", "nb_traj_destroy",
     "nb_ensemble_run", "nb_solve", "nb_solve_trajectory_count", "nb_solve_partial", "nb_solve_combine",
     "nb_profile_enable", "nb_profile_read", "nb_read_header", "nb_read_input", "nb_write_output", "nb_write_input", "nb_generate_system", "nb_hw5_main",
@@ -75,6 +75,22 @@ ABI_SYMBOLS = [
     "nb_sym_create", "nb_sym_destroy", "nb_sym_pj_bytes", "nb_sym_counter_bytes", "nb_sym_blocks", "nb_sym_remote_partial_bytes",
     "nb_sym_pairs", "nb_sym_wait_positions", "nb_sym_step", "nb_sym_step_phase", "nb_sym_plan_describe", "nb_sym_rows", "nb_sym_row_size", "nb_device_warm", "nb_hw5_narrow_visible_gpus", "nb_sym_publish_rows", "nb_sym_unpack_rows",
 ]
+
+class _Missing:
+    def __call__(self, *a):
+        raise NbodyError(NB_ERR_UNSUPPORTED, "entry point missing in this build of the library")
+
+
+class _Tolerant:
+    def __init__(self, L):
+        object.__setattr__(self, "_L", L)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._L, name)
+        except AttributeError:
+            return _Missing()
+
 
 _lib_handle = None
 _dp = C.POINTER(C.c_double)
@@ -91,12 +107,15 @@ def lib():
         raise ImportError("libnbody_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(or make -C %s/csrc); there is no CPU fallback" % _HERE)
     L = C.CDLL(LIB_PATH)
+    if os.environ.get("NB_LIB_TOLERANT"):  # tools only: A/B runs against an older build that lacks newer entry points
+        L = _Tolerant(L)
     L.nb_version.restype = C.c_char_p
     L.nb_strerror.restype = C.c_char_p
     L.nb_strerror.argtypes = [C.c_int]
     L.nb_last_error_detail.restype = C.c_char_p
     L.nb_device_count.argtypes = [_ip]
     L.nb_kernel_launches.restype = C.c_longlong
+    L.nb_grid_torn_records.restype = C.c_longlong
     L.nb_run_steps.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _up, C.c_int, C.c_int]
     L.nb_traj_create.argtypes = [C.c_int, C.POINTER(NbSystem), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.nb_traj_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(NbEvents)]
@@ -220,6 +239,11 @@ def device_count():
 
 def kernel_launches():
     return int(lib().nb_kernel_launches())
+
+
+def grid_torn_records():
+    """Torn 32-byte records the grid kernel's exchange detected and fetched again in this process (expected 0)."""
+    return int(lib().nb_grid_torn_records())
 
 
 def read_input(path):

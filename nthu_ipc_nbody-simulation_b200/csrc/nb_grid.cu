@@ -9,7 +9,7 @@
 // latency is  hop (publish -> everybody has it)  +  pair loop  +  reduction/integration,  and the design goal
 // is a hop of about one L2 round trip:
 //
-//   * publish: a body leaves as one naturally aligned 32-byte sector {x, y, z, step tag} (one 256-bit store)
+//   * publish: a body leaves as one naturally aligned 32-byte sector {x, y, z, self-checking tag} (one 256-bit store)
 //     into a global record array double-buffered by step parity (L2 resident).  No fence, no atomic, no flag:
 //     a sector is the unit the L2 reads and writes, so a reader sees it entirely old or entirely new and the
 //     tag validates the data it travels with.
@@ -138,27 +138,32 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 template <int NTHREADS>
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-// Record layout: one 32-byte sector {x, y, z, tag}.  The tag is SELF-CHECKING: step XOR a fold of the bit patterns of
-// x, y and z, so a record is accepted only if all four words belong together.  The design relies on a naturally aligned
-// 32-byte access being one L2 sector transaction (see the header comment), which the PTX memory model does not promise
-// for vector or bulk accesses; with this tag a torn record - any mixture of words of two publications - fails the
-// check (up to a 2^-64 coincidence) and is polled again instead of being consumed.
-__device__ __forceinline__ unsigned long long fold3(double x, double y, double z) {
-    const unsigned long long a = (unsigned long long)__double_as_longlong(x), b = (unsigned long long)__double_as_longlong(y),
-                             c = (unsigned long long)__double_as_longlong(z);
-    return a ^ ((b << 21) | (b >> 43)) ^ ((c << 42) | (c >> 22));
+// Record layout: one 32-byte sector {x, y, z, tag}.  The tag is SELF-CHECKING: step in the upper 32 bits, a 32-bit
+// fold of the bit patterns of x, y and z in the lower 32, so a record is accepted only if all four words belong
+// together.  The design relies on a naturally aligned 32-byte access being one L2 sector transaction (see the header
+// comment), which the PTX memory model does not promise for vector or bulk accesses; with this tag a torn record - any
+// mixture of words of two publications - fails the check (up to a 2^-32 coincidence per torn record) and is fetched
+// again instead of being consumed.  Two checks: the STEP check needs the tag word only (a record that was copied
+// before its publication is old in all four words: the common case, handled in the validation pass); both are made in
+// the validation pass (validate_stage, kept out of line so that the pair loop's code generation does not depend on it).
+__device__ __forceinline__ unsigned fold32(double x, double y, double z) {
+    const unsigned lx = (unsigned)__double2loint(x), hx = (unsigned)__double2hiint(x), ly = (unsigned)__double2loint(y),
+                   hy = (unsigned)__double2hiint(y), lz = (unsigned)__double2loint(z), hz = (unsigned)__double2hiint(z);
+    return lx ^ __funnelshift_l(hx, hx, 5) ^ __funnelshift_l(ly, ly, 11) ^ __funnelshift_l(hy, hy, 17) ^
+           __funnelshift_l(lz, lz, 23) ^ __funnelshift_l(hz, hz, 29);
 }
 __device__ __forceinline__ double make_tag(int step, double x, double y, double z) {
-    return __longlong_as_double((long long)((unsigned long long)(long long)step ^ fold3(x, y, z)));
+    return __hiloint2double(step, (int)fold32(x, y, z));
 }
+__device__ __forceinline__ bool tag_step_is(double tg, int step) { return __double2hiint(tg) == step; }
 __device__ __forceinline__ bool tag_ok(double tg, int step, double x, double y, double z) {
-    return (unsigned long long)__double_as_longlong(tg) == ((unsigned long long)(long long)step ^ fold3(x, y, z));
+    return __double2hiint(tg) == step && (unsigned)__double2loint(tg) == fold32(x, y, z);
 }
 
 struct Shared {
     // stage = step parity.  full: the copies of all R records have landed (1 arrival = the producer's expect_tx, plus
     // the bytes); obs: the observer has judged the step (1 arrival).  Each completes once per two steps.
-    alignas(8) uint64_t full[MAX_T][2][MAX_CS];  // one per slice of the exchange (cluster rank), see below
+    alignas(8) uint64_t full[MAX_T][2];
     alignas(8) uint64_t obs[MAX_T][2];
     alignas(8) uint64_t trig[MAX_T][2];  // producer trigger: this block's sums of the step are complete (1 arrival)
     volatile int flags[MAX_T][2];   // FLAG_* of the step held by the stage, valid once obs completed
@@ -176,11 +181,57 @@ struct ObsState {  // per system, observer warp
     double my_m0;
 };
 
+// The validation pass of the compute warps (256 threads, thread tid checks records tid + 256k): every record of the stage
+// must pass the FULL self-check for step `st`.  A record that does not was copied before its publication (stale: the
+// common case, and how the fast blocks wait for the slowest) or is torn: its thread polls that sector in global memory
+// until it passes and patches shared memory.  A function of its own (A/B: -DNB_GRID_VALIDATE_ATTR=__noinline__): the FP64 pair
+// loop's register allocation is sensitive to what is inlined around it (measured on B200, b1024, us per step: validation
+// written inline in the step loop 3.80, this function force-inlined 3.40, out of line 3.49; round 1's tag-only check 3.21).
+#ifndef NB_GRID_VALIDATE_ATTR
+#define NB_GRID_VALIDATE_ATTR __forceinline__
+#endif
+__device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* grec, int R, int st, int tid, int hsel, volatile int* abort_flag,
+                                            int* status, unsigned long long* n_stale) {
+    bool patched = false;
+    double2 va[4], vb[4];  // whole records, conflict-free LDS.128 pairs (lanes with bit 2 set read the second half first)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = min(tid + 256 * k, R - 1);
+        va[k] = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
+        vb[k] = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = tid + 256 * k;
+        const double2 lo = hsel ? vb[k] : va[k], hi = hsel ? va[k] : vb[k];
+        if (r < R && !tag_ok(hi.y, st, lo.x, lo.y, hi.x)) {
+            double x, y, z, tg;
+            const long long t0 = clock64();
+            do {
+                ld_sector(grec + 4 * (size_t)r, x, y, z, tg);
+                if (*abort_flag) break;
+                if (clock64() - t0 > SPIN_LIMIT) {
+                    *abort_flag = 1;
+                    atomicExch(status, 1);
+                    break;
+                }
+            } while (!tag_ok(tg, st, x, y, z));
+            if (tag_step_is(hi.y, st)) atomicAdd(status + 1, 1);  // right step, wrong fold: a TORN record (word 1 of the status block)
+            pos[4 * r] = x, pos[4 * r + 1] = y, pos[4 * r + 2] = z;
+            __threadfence_block();
+            pos[4 * r + 3] = tg;
+            patched = true;
+            (*n_stale)++;
+        }
+    }
+    return patched;
+}
+
 // PROFILE: block 0 thread 0 accumulates clock64 per phase (NB_GRID_PROFILE=1)
 template <int MATH, int T, int NJ, bool PROFILE>
 __global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single, int groups) {
+                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single) {
     extern __shared__ __align__(128) double smem[];
     __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -206,7 +257,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             // a trajectory that stopped in an earlier launch never steps again
             sh.stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
             for (int b = 0; b < 2; b++) {
-                for (int sl = 0; sl < MAX_CS; sl++) mbar_init(&sh.full[t][b][sl], 1);
+                mbar_init(&sh.full[t][b], 1);
                 mbar_init(&sh.obs[t][b], 1);
                 mbar_init(&sh.trig[t][b], 1);
                 sh.flags[t][b] = 0;
@@ -254,12 +305,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 atomicExch(status, 1);
                 break;
             }
-        } while (!tag_ok(tg, st, x, y, z));
+        } while (!tag_ok(tg, st, x, y, z));  // the FULL self-check: all four words of one publication
     };
     // A record of step `st` for the observer: out of shared memory if it passes the self-check, else out of global memory.
     auto load_rec = [&](const double* pos, const double* grec, int r, int st, double& x, double& y, double& z) {
-        // The compute warps patch stale shared-memory records word by word (patch_rec): a record caught half patched
-        // fails the self-check like any torn record and is fetched from global memory instead.
+        // a record caught half patched by a compute thread (patch_rec) fails the self-check like any torn record and is
+        // fetched from global memory instead
         const volatile double* vp = pos + 4 * r;
         double tg = vp[3];
         x = vp[0], y = vp[1], z = vp[2];
@@ -318,10 +369,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         continue;
                     }
                     const long long t1 = clock64();
-                    // slice s of the record array arrives from cluster rank s (its multicast) on mbarrier s of every block:
-                    // arm all of this block's slice barriers, then copy this rank's slice into everybody
-                    for (uint32_t sl = 0; sl < CS; sl++) mbar_arrive_expect_tx(&sh.full[t][st & 1][sl], slice * 32u);
-                    uint64_t* bar = &sh.full[t][st & 1][rank];
+                    uint64_t* bar = &sh.full[t][st & 1];
+                    mbar_arrive_expect_tx(bar, (uint32_t)R * 32u);
                     // Copy delay after the trigger: long enough for everybody's sectors of this step to be in the L2 when the
                     // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
                     // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
@@ -378,11 +427,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 ObsState& s = os[t];
                 if (!s.active) continue;
                 const int st = s.step, stage = st & 1;
-                bool landed = true;
-                if (st > s.step_begin)
-                    for (uint32_t sl = 0; sl < cluster_nctarank() && landed; sl++)
-                        landed = wait_bar(&sh.full[t][stage][sl], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u);
-                if (!landed) {
+                if (st > s.step_begin && !wait_bar(&sh.full[t][stage], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u)) {
                     s.active = false;
                     continue;
                 }
@@ -465,24 +510,13 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         const int bg = warp / NJ, part = warp % NJ;
         const int body0 = c * GB + bg * BPW;  // the warp's four bodies (records body0 .. body0+3)
         const int hsel = (lane >> 2) & 1;     // conflict-free LDS.128 pairs: these lanes read the second half first
-        // Every warp integrates ITS four bodies itself (lanes 0..11: body lane/3, component lane%3; the NJ warps of a body
-        // group do identical arithmetic on identical inputs), so the positions of the own bodies never wait for the
-        // exchange and no second block barrier is needed; the warp with part == 0 publishes.
-        const int wb = lane / 3, wk = lane - 3 * wb;
-        const int w_body = body0 + wb;
-        const bool winteg = lane < 3 * BPW;
-        // the exchange lands slice by slice (one slice per cluster rank, one mbarrier each): when a slice is a whole number
-        // of warp strides the pair loop starts on slice 0 while the others are still in flight
-        const int CSn = (int)cluster_nctarank();
-        const int slice = R / CSn;
-        // groups of spg slices are waited for, validated and consumed one after another (groups <= 0: one group = the
-        // un-pipelined exchange; the padded tail of the stage, zero mass, belongs to the single group only)
-        int G = groups > 0 && groups <= CSn && CSn % groups == 0 && ((slice * (CSn / groups)) % RQ) == 0 ? groups : 1;
-        const int spg = CSn / G;
-        const int gsize = G > 1 ? slice * spg : RS;
+        // integrator threads (warp 0, lane < 24): body 8c + lane/3, component lane%3
+        const int ib = lane / 3, ik = lane - 3 * ib;
+        const int my_body = c * GB + ib;
+        const bool integ = warp == 0 && lane < 3 * GB;
         int cstep[T], cbegin[T], cend[T];
         bool cact[T];
-        double wq[T], wv[T];
+        double iq[T], iv[T];
         long long pacc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
         unsigned long long n_stale = 0;
         auto tick = [&](int phase) {
@@ -498,9 +532,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             const TrajDesc& d = descs[t];
             cstep[t] = cbegin[t] = d.step_begin, cend[t] = d.step_end;
             cact[t] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
-            const bool mine = winteg && w_body < n;
-            wq[t] = mine ? d.q[wk * n + w_body] : 0.0;
-            wv[t] = mine ? d.v[wk * n + w_body] : 0.0;
+            const bool mine = integ && my_body < n;
+            iq[t] = mine ? d.q[ik * n + my_body] : 0.0;
+            iv[t] = mine ? d.v[ik * n + my_body] : 0.0;
             any |= cact[t];
         }
         long long g0 = 0, c0 = 0;
@@ -518,67 +552,47 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 if (PROFILE) pt = clock64();
                 const int st = cstep[t], stage = st & 1;
                 const bool last = st >= cend[t];
+                // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
+                if (!last && st > cbegin[t]) wait_bar(&sh.full[t][stage], (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u);
+                tick(0);
                 double* pos = s_pos(t, stage);
                 const double* cg = s_gm(t, stage);
                 const double* grec = g_rec(t, st);
-                const uint32_t fpar = (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u;
                 double ax[BPW], ay[BPW], az[BPW];
                 int flags = 0;
+                if (!last) {
+                    // (0) validate: every record of the stage must carry this step's tag (thread tid checks records
+                    //     tid + 256k; the tags of 32 consecutive records share 8 banks, so this pass is shared-memory bound: ~256 clk at
+                    //     n = 1024).  A stale record was copied
+                    //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
+                    //     memory and patch shared memory, each stale record by exactly one thread of the block.
+                    const bool patched = validate_stage(pos, grec, R, st, tid, hsel, &sh.abort, status, &n_stale);
+                    // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
+                    if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    compute_bar<32 * NCW>();
+                }
+                tick(5);
                 for (int attempt = 0; attempt < 2; attempt++) {
 #pragma unroll
                     for (int i = 0; i < BPW; i++) ax[i] = ay[i] = az[i] = 0.0;
                     if (!last) {
-                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records.  The own
-                        //     positions come out of the warp's integrator lanes, not out of the exchange.
+                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records
                         double xi[BPW], yi[BPW], zi[BPW];
 #pragma unroll
                         for (int i = 0; i < BPW; i++) {
-                            xi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i);
-                            yi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i + 1);
-                            zi[i] = __shfl_sync(0xffffffffu, wq[t], 3 * i + 2);
+                            const double* p = pos + 4 * (body0 + i);
+                            xi[i] = p[0], yi[i] = p[1], zi[i] = p[2];
                         }
-                        for (int g = 0; g < G; g++) {
-                            // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
-                            if (st > cbegin[t])
-                                for (int sl = g * spg; sl < (g + 1) * spg; sl++) wait_bar(&sh.full[t][stage][sl], fpar);
-                            if (g == 0) tick(0);
-                            // (0) validate the group that has just landed, all 256 threads in parallel (thread tid checks records
-                            //     tid + 256k of the group): a record that was copied before its publication, or torn, fails the
-                            //     self-check - this is how the fast blocks wait for the slowest.  Poll that sector in global
-                            //     memory and patch shared memory, each stale record by exactly one thread of the block; the
-                            //     polls of a group overlap, so a late block costs everybody one L2 round trip, not one per record.
-                            bool patched = false;
-                            for (int i = tid; i < gsize; i += 32 * NCW) {
-                                const int r = g * gsize + i;
-                                if (r < R) {
-                                    const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
-                                    const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
-                                    const double2 lo = hsel ? B : A, hi = hsel ? A : B;
-                                    if (!tag_ok(hi.y, st, lo.x, lo.y, hi.x)) {
-                                        patch_rec(pos, grec, r, st);
-                                        patched = true;
-                                        n_stale++;
-                                    }
-                                }
-                            }
-                            // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
-                            if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            compute_bar<32 * NCW>();
-                            if (g == 0) tick(5);
 #pragma unroll 2
-                            for (int i = 32 * part + lane; i < gsize; i += RQ) {
-                                const int r = g * gsize + i;
-                                // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
-                                const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
-                                const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
-                                const double jx = hsel ? B.x : A.x, jy = hsel ? B.y : A.y, jz = hsel ? A.x : B.x;
-                                const double jg = cg[r];
+                        for (int r = 32 * part + lane; r < RS; r += RQ) {
+                            // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
+                            const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
+                            const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
+                            const double jx = hsel ? B.x : A.x, jy = hsel ? B.y : A.y, jz = hsel ? A.x : B.x;
+                            const double jg = cg[r];
 #pragma unroll
-                                for (int b = 0; b < BPW; b++) pair<MATH>(xi[b], yi[b], zi[b], jx, jy, jz, jg, ax[b], ay[b], az[b]);
-                            }
+                            for (int i = 0; i < BPW; i++) pair<MATH>(xi[i], yi[i], zi[i], jx, jy, jz, jg, ax[i], ay[i], az[i]);
                         }
-                    } else {
-                        tick(0);
                     }
                     tick(1);
                     // (2) the observer's verdict on the positions of step st
@@ -626,26 +640,25 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     }
                 }
                 tick(3);
-                compute_bar<32 * NCW>();  // the only block barrier of a step: the j-parts meet
+                compute_bar<32 * NCW>();
                 if (sh.abort) {  // an exchange wait timed out somewhere in this block
                     aborted = true;
                     break;
                 }
-                // (4) a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88) in every warp; the part-0 warp of a
-                //     body group publishes each body as one self-checking sector {x, y, z, tag}, unfenced
-                if (tid == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
-                if (winteg) {
-                    const double* p = &sh.part[pbuf][bg * NJ][3 * wb + wk];
-                    double a = p[0];
+                // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
+                //     tagged sector {x, y, z, step}, unfenced
+                if (warp == 0) {
+                    if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
+                    if (integ) {
+                        const double* p = &sh.part[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
+                        double a = p[0];
 #pragma unroll
-                    for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
-                    if (w_body < n) kick_drift(a, wv[t], wq[t]);
-                }
-                {
-                    const double qy = __shfl_down_sync(0xffffffffu, wq[t], 1);
-                    const double qz = __shfl_down_sync(0xffffffffu, wq[t], 2);
-                    if (part == 0 && winteg && wk == 0)
-                        st_sector(g_rec(t, st + 1) + 4 * (size_t)w_body, wq[t], qy, qz, make_tag(st + 1, wq[t], qy, qz));
+                        for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
+                        if (my_body < n) kick_drift(a, iv[t], iq[t]);
+                    }
+                    const double qy = __shfl_down_sync(0xffffffffu, iq[t], 1);
+                    const double qz = __shfl_down_sync(0xffffffffu, iq[t], 2);
+                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[t], qy, qz, make_tag(st + 1, iq[t], qy, qz));
                 }
                 cstep[t] = st + 1;
                 pbuf ^= 1;
@@ -671,12 +684,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         }
         if (PROFILE && n_stale) atomicAdd((unsigned long long*)&prof[5], n_stale);
         // write back
-        if (part == 0 && winteg && w_body < n) {
+        if (integ && my_body < n) {
 #pragma unroll
             for (int t = 0; t < T; t++) {
                 const TrajDesc& d = descs[t];
-                d.q[wk * n + w_body] = wq[t];
-                d.v[wk * n + w_body] = wv[t];
+                d.q[ik * n + my_body] = iq[t];
+                d.v[ik * n + my_body] = iv[t];
             }
         }
     }
@@ -783,14 +796,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         }
     }
     const auto h0 = std::chrono::steady_clock::now();
-    // pipeline depth of the exchange: 1 = wait for all slices, then validate and compute (default); 2 / 4 = consume the
-    // slices group by group as they land.  Measured on B200, b1024 (profiles/r02_grid_pipeline.md): 3.80 / 4.49 / 4.87
-    // us per step at delay 900 - the blocks keep in step only through the data, and with a validate + barrier per group a
-    // block that polls in one group is late for the next, whose records the others then find stale (30 000 stale records
-    // per step against 5 000): the pipeline loses more in polls than it hides in copy time.
-    static const int groups_env = env_int("NB_GRID_GROUPS", 1);
-    int groups = groups_env;
-    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single, groups));
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single));
     count_launch();
     {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
@@ -809,7 +815,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         fprintf(stderr, "grid kernel %.3f ms by events | block entry spread %.1f us | first entry -> last block done %.3f ms | block done spread %.1f us\n",
                 kms, (h[9] - h[8]) * 1e-3, (h[11] - h[8]) * 1e-6, (h[11] - h[10]) * 1e-3);
         fprintf(stderr,
-                "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait first group %lld | validate first group %lld | pairs + later groups %lld | wait observer %lld | "
+                "grid profile T=%d NJ=%d CS=%d delay=%d (clk, block 0 thread 0): wait copy %lld | validate %lld | pairs %lld | wait observer %lld | "
                 "butterfly %lld | barrier+integrate+publish %lld | stale records polled (all blocks) %lld | SM clock %lld MHz\n",
                 T, NJ, cs, delay_clk, h[0], h[6], h[1], h[2], h[3], h[4], h[5], h[7]);
     }

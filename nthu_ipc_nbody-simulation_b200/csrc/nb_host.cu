@@ -32,6 +32,7 @@ static std::atomic<long long> g_launches{0};
 // set by nb_hw5_main: the process leaves through _exit right after the output file is written, so device buffers,
 // pinned mailboxes and streams are not torn down one by one (cudaFree / cudaFreeHost cost up to 0.7 s there)
 std::atomic<bool> g_leak_on_exit{false};
+static std::atomic<long long> g_torn_records{0};
 void count_launch(int n) { g_launches += n; }
 
 // ---- |sin(step*dt/6000)| table ----------------------------------------------------------------------
@@ -245,7 +246,8 @@ struct DeviceBatch {
         }
         NB_CUDA(cudaMemcpyAsync(pin_ev, ev, S * sizeof(nb_events), cudaMemcpyDeviceToHost, stream));
         *pin_status = 0;
-        if (grid) NB_CUDA(cudaMemcpyAsync(pin_status, grid_traj_status(grid_ws, n), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        pin_status[1] = 0;
+        if (grid) NB_CUDA(cudaMemcpyAsync(pin_status, grid_traj_status(grid_ws, n), 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         // Busy-wait instead of cudaStreamSynchronize: the blocking wait costs tens of milliseconds of wake-up latency now
         // and then (measured on the B200 boxes), and the chain plan of nb_solve comes through here every few thousand steps.
         for (;;) {
@@ -254,6 +256,7 @@ struct DeviceBatch {
             if (qe != cudaErrorNotReady) return cuda_fail(qe, "cudaStreamQuery", __FILE__, __LINE__);
         }
         memcpy(h_ev.data(), pin_ev, S * sizeof(nb_events));
+        if (pin_status[1] != 0) g_torn_records += pin_status[1];  // records that failed the full self-check and were fetched again
         if (*pin_status != 0) {
             set_error_detail("grid trajectory kernel: exchange spin timed out (blocks not co-resident?)");
             return NB_ERR_CUDA;
@@ -321,6 +324,7 @@ int nb_device_count(int* count) {
 }
 
 long long nb_kernel_launches(void) { return nb::g_launches.load(); }
+long long nb_grid_torn_records(void) { return nb::g_torn_records.load(); }
 
 // Everything a GPU needs before its first trajectory launch, callable from a helper thread while the input is still
 // being parsed: driver initialisation + primary context, the |sin| table, the trajectory kernels' module.

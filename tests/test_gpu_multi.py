@@ -18,7 +18,7 @@ nb = importlib.import_module("nthu_ipc_nbody-simulation_b200")
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-n, steps = 4096, 6
+n, steps = 6144, 6
 s = nb.synthetic_system(n, seed=21)
 sh = nb.ShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
 sh.advance(steps)
@@ -29,12 +29,36 @@ pp.advance(steps)
 qp, vp = pp.positions(), pp.velocities()
 pp.close()
 p2p_equal = bool(np.array_equal(q, qp) and np.array_equal(v, vp))
+# the symmetric stepper over real peer mappings (CUDA IPC): partial rows + pos4 rows stored into the peers, in-kernel waits
+def close(qa, va, qb, vb):
+    return bool(np.abs(qa - qb).max() <= max(1e-12 * np.abs(vb).max() * 60.0, 2 * np.spacing(np.abs(qb)).max())
+                and np.allclose(va, vb, rtol=1e-12, atol=0))
+sy = nb.SymShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
+sy.advance(steps)
+qs, vs = sy.positions(), sy.velocities()
+sy.close()
+sy2 = nb.SymShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
+sy2.advance(steps)
+qs2, vs2 = sy2.positions(), sy2.velocities()
+# e2e operator: host buffers in, host buffers out, same state
+ib, ic = sy2.i_begin, sy2.i_count
+sy3 = nb.SymShardedSystem(s, rank=rank, world=world, device="cuda:%%d" %% local)
+qh = torch.from_numpy(s.q.reshape(3, n)[:, ib:ib + ic].copy()).pin_memory()
+vh = torch.from_numpy(s.v.reshape(3, n)[:, ib:ib + ic].copy()).pin_memory()
+for _ in range(steps):
+    sy3.step_host(qh, vh)
+host_equal = bool(np.array_equal(qh.numpy(), qs.reshape(3, n)[:, ib:ib + ic]) and np.array_equal(vh.numpy(), vs.reshape(3, n)[:, ib:ib + ic]))
+sy2.close(); sy3.close()
+flags = torch.tensor([close(qs, vs, q, v), np.array_equal(qs, qs2) and np.array_equal(vs, vs2), host_equal], dtype=torch.int32, device="cuda:%%d" %% local)
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+sym_close, sym_deterministic, sym_host = [bool(x) for x in flags.tolist()]
 case = nb.read_input(%(case)r)
 ans, secs, pairs = nb.solve_distributed(case, rank, world, local)
 if rank == 0:
     q1, v1 = s.q.copy(), s.v.copy()
     nb.run_steps(0, steps, n, q1, v1, s.m, s.is_device, gpu=local)
-    print(json.dumps(dict(p2p_equal=p2p_equal, sharded_equal=bool(np.array_equal(q, q1) and np.array_equal(v, v1)),
+    print(json.dumps(dict(sym_close=sym_close, sym_deterministic=sym_deterministic, sym_host=sym_host,
+                          sym_vs_one_gpu=close(qs, vs, q1, v1), p2p_equal=p2p_equal, sharded_equal=bool(np.array_equal(q, q1) and np.array_equal(v, v1)),
                           text=nb.format_output(ans.min_dist, ans.hit_time_step, ans.gravity_device_id, ans.missile_cost),
                           n_traj=ans.n_trajectories)))
 dist.destroy_process_group()
@@ -54,6 +78,9 @@ def test_two_gpus_sharded_and_ensemble(nb, tmp_path):
     out = json.loads([l for l in r.stdout.decode().split("\n") if l.startswith("{")][-1])
     assert out["sharded_equal"]
     assert out["p2p_equal"]  # P2P-store exchange == NCCL all-gather exchange, bit for bit
+    # symmetric stepper on two GPUs: == the row-kernel NCCL path and the one-GPU run at the FAST tolerance, run-to-run
+    # bit-identical, and the host-buffer operator (step_host) leaves the same state as the resident run
+    assert out["sym_close"] and out["sym_vs_one_gpu"] and out["sym_deterministic"] and out["sym_host"]
     g = golden_lines("b200")
     a, b, c = out["text"].split("\n")[:3]
     assert b == str(g["hit_time_step"]) and c == g["text"].split("\n")[2]

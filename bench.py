@@ -383,6 +383,7 @@ def run_ours(args):
     n = args.n
     system = nb.synthetic_system(n, seed=42)
     sh = make_system(nb, args.exchange, system, rank, world, dev)
+    exchange_bytes = sh.bytes_exchanged_per_step()
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
@@ -566,7 +567,7 @@ def run_ours(args):
                                if args.exchange == "sym" else "fast (16 FP64 instr per ordered pair)",
                        "parallelism": "body-sharded x%d" % world, "exchange": exch if world > 1 else "none (1 GPU)",
                        "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB memset, outside the per-step events)",
-                       "exchange_bytes_per_rank_per_step": sh.bytes_exchanged_per_step()},
+                       "exchange_bytes_per_rank_per_step": exchange_bytes},
             "frac_of_fp64_peak": value * PAIR_FLOPS / (world * FP64_PEAK_NOMINAL_TFLOPS * 1e12),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_NOMINAL_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_NOMINAL_TFLOPS,

@@ -276,6 +276,7 @@ int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, i
                          long long* onesided_pairs);
 int nb_sym_row_size(void);         /* bodies per row (= i-bodies per thread block) of this build */
 int nb_sym_rows(int n, int world); /* rows per rank */
+int nb_sym_row_stride(int n, int world); /* bodies per row: the shard spread evenly over the fewest rows */
 
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* long independent DFMA chains on every SM: measured FP64 peak of this GPU in TFLOP/s */

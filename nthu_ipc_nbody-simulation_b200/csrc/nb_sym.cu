@@ -46,41 +46,47 @@ struct Span {
     int src;         // rank that owns [j0, j1)
 };
 
-int rows_of(int shard) { return (shard + SB - 1) / SB; }
+// The bodies of a shard are spread EVENLY over the fewest rows that hold them: a row always occupies all SB register slots
+// of its block (a short row leaves lanes idle but takes as long per j body), so rows of equal length keep the cost of a
+// (row, j) unit uniform.  stride = bodies per row.
+int stride_of(int shard) {
+    const int rows = (shard + SB - 1) / SB;
+    return (shard + rows - 1) / rows;
+}
+int rows_of(int shard) { return (shard + stride_of(shard) - 1) / stride_of(shard); }
 
 // the spans of rank p, phase by phase (phase 0 = local, phase 1 = remote)
 void spans_of_rank(int n, int world, int p, std::vector<std::vector<Span>>& phases) {
-    const int S = n / world, R = rows_of(S), base = p * S;
-    auto cnt = [&](int r) { return std::min(S, (r + 1) * SB) - r * SB; };
+    const int S = n / world, R = rows_of(S), base = p * S, RS = stride_of(S);
+    auto cnt = [&](int r) { return std::min(S, (r + 1) * RS) - r * RS; };
     phases.assign(2, {});
     for (int r = 0; r < R; r++) {
-        const int r1 = std::min(S, (r + 1) * SB);
-        if (r1 < S) phases[0].push_back({r * SB, cnt(r), base + r1, base + S, false, p});  // the rows behind it, symmetric
-        phases[0].push_back({r * SB, cnt(r), base + r * SB, base + r1, true, p});           // its own bodies, one-sided
+        const int r1 = std::min(S, (r + 1) * RS);
+        if (r1 < S) phases[0].push_back({r * RS, cnt(r), base + r1, base + S, false, p});  // the rows behind it, symmetric
+        phases[0].push_back({r * RS, cnt(r), base + r * RS, base + r1, true, p});           // its own bodies, one-sided
     }
     if (world == 1) return;
     const int full = (world - 1) / 2;  // partners evaluated entirely by this rank
     for (int k = 1; k <= full; k++) {
         const int q = (p + k) % world;
-        for (int r = 0; r < R; r++) phases[1].push_back({r * SB, cnt(r), q * S, q * S + S, false, q});
+        for (int r = 0; r < R; r++) phases[1].push_back({r * RS, cnt(r), q * S, q * S + S, false, q});
     }
     if (world % 2 == 0) {
-        // the block pair (lo, hi = lo + P/2) is shared half and half: lo takes every row of its shard against the first h
-        // bodies of hi; hi takes its bodies from h on against all of lo.  h need not be a row boundary: hi's first row
-        // is then a partial ("virtual") row [h, next boundary), and the part of lo's partial row in hi's PJ that nobody
-        // writes stays zero (PJ buffers are zero-filled once).
+        // The block pair (lo, hi = lo + P/2) is shared half and half IN TIME (a row costs the same per j body whatever its
+        // length): hi takes its rows behind rb against all of lo, lo takes all its rows against the bodies of hi's rows
+        // before rb; with an odd number of rows, hi's row rb is split down the middle of lo: hi takes it against lo's
+        // rows from cr on, lo takes its rows before cr against it.  Every cut lies on a row boundary of the owner of the
+        // a_j partials, so a PJ row is written entirely or not at all for each row of its owner.
         const int q = (p + world / 2) % world;
-        const int h = (S / 2) / SUB * SUB;
-        if (p < q) {
-            if (h > 0)
-                for (int r = 0; r < R; r++) phases[1].push_back({r * SB, cnt(r), q * S, q * S + h, false, q});
-        } else {
-            int i0 = h;
-            while (i0 < S) {
-                const int i1 = std::min(S, (i0 / SB + 1) * SB);
-                phases[1].push_back({i0, i1 - i0, q * S, q * S + S, false, q});
-                i0 = i1;
-            }
+        const int rb = R / 2, cr = (R % 2) ? (R + 1) / 2 : 0;
+        const int hb = std::min(S, rb * RS), hb1 = std::min(S, (rb + 1) * RS), cb = std::min(S, cr * RS);
+        if (p < q) {  // this rank is lo
+            if (hb > 0)
+                for (int r = 0; r < R; r++) phases[1].push_back({r * RS, cnt(r), q * S, q * S + hb, false, q});
+            for (int r = 0; r < cr; r++) phases[1].push_back({r * RS, cnt(r), q * S + hb, q * S + hb1, false, q});
+        } else {      // this rank is hi
+            if (R % 2) phases[1].push_back({rb * RS, cnt(rb), q * S + cb, q * S + S, false, q});
+            for (int r = rb + (R % 2); r < R; r++) phases[1].push_back({r * RS, cnt(r), q * S, q * S + S, false, q});
         }
     }
 }
@@ -92,6 +98,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
     P.n = n, P.world = world, P.rank = rank, P.blocks = blocks;
     P.shard = n / world;
     P.rows_local = rows_of(P.shard);
+    P.row_stride = stride_of(P.shard);
     P.rows_global = world * P.rows_local;
     const int S = P.shard, base = rank * S;
     std::vector<std::vector<Span>> phases;
@@ -100,9 +107,10 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
     std::vector<double> got(blocks, 0.0);  // cost given to each block so far
     double ideal_before = 0;               // what an exact split of the earlier phases would have given it
     for (const auto& spans : phases) {
-        // cost of one SUB-wide unit of a span = bodies of the row x weight (one-sided: 16 instr per ordered pair, no
-        // rotation, against 20 per unordered pair)
-        auto unit_cost = [&](const Span& s) { return s.icount * (s.onesided ? 0.8 : 1.0); };
+        // cost of one SUB-wide unit of a span: a row occupies all SB register slots of the block however many bodies it
+        // has, so the time per j body is the same for every row (one-sided: 16 instr per ordered pair, no rotation,
+        // against 20 per unordered pair)
+        auto unit_cost = [&](const Span& s) { return SB * (s.onesided ? 0.8 : 1.0) + 0.0 * s.icount; };
         double total = 0;
         for (const auto& s : spans) total += unit_cost(s) * ((s.j1 - s.j0 + SUB - 1) / SUB);
         if (total <= 0) continue;
@@ -144,7 +152,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
                 g.j1 = std::min(s.j1, s.j0 + (u0 + take) * SUB);
                 g.flags = s.onesided ? SEG_ONESIDED : 0;
                 g.pi_slot = -1;
-                g.pj_row = rank * P.rows_local + s.i0 / SB;  // a virtual row takes the number of the aligned row around it
+                g.pj_row = rank * P.rows_local + s.i0 / P.row_stride;  // a virtual row takes the number of the aligned row around it
                 g.src_rank = s.src;
                 per_block[k].push_back(g);
                 if (s.onesided)
@@ -179,7 +187,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
             if (i == 0 || !same_row(v[i - 1], v[i])) v[i].flags |= SEG_LOAD;
             if (i + 1 == v.size() || !same_row(v[i + 1], v[i])) {
                 v[i].flags |= SEG_FLUSH;
-                flushes.push_back({(v[i].row_body0 - base) / SB, b, (int)i});
+                flushes.push_back({(v[i].row_body0 - base) / P.row_stride, b, (int)i});
             }
         }
     }
@@ -211,8 +219,8 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
             for (const auto& s : spans) {
                 if (s.onesided || s.src != rank) continue;
                 for (int c = 0; c < P.rows_local; c++) {
-                    const int c0 = base + c * SB, c1 = base + std::min(S, (c + 1) * SB);
-                    if (s.j0 < c1 && s.j1 > c0) contrib[c].push_back(p * P.rows_local + s.i0 / SB);
+                    const int c0 = base + c * P.row_stride, c1 = base + std::min(S, (c + 1) * P.row_stride);
+                    if (s.j0 < c1 && s.j1 > c0) contrib[c].push_back(p * P.rows_local + s.i0 / P.row_stride);
                 }
             }
     }
@@ -469,7 +477,7 @@ struct IntegrateArgs {
     const double* pi;
     const double* pj;  // own PJ
     const int *pi_ptr, *pi_list, *pj_ptr, *pj_list;
-    int shard, i_begin;
+    int shard, i_begin, row_stride;
     double fst_next;
     int parity;                     // of this step: partial counters waited on, position counters raised
     unsigned long long acc_target;  // 0 = nothing to wait for (one rank)
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(128) sym_integrate_kernel(IntegrateArgs A, Pee
     }
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il < A.shard) {
-        const int row = il / SB;
+        const int row = il / A.row_stride;
         double a[3] = {0.0, 0.0, 0.0};
         for (int s = A.pi_ptr[row]; s < A.pi_ptr[row + 1]; s++) {
             // {slot, first local body, bodies} of a row run that covers (part of) this aligned row
@@ -634,7 +642,8 @@ int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, i
 }
 
 int nb_sym_row_size(void) { return SB; }
-int nb_sym_rows(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : (n / world + SB - 1) / SB; }
+int nb_sym_rows(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : rows_of(n / world); }
+int nb_sym_row_stride(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : stride_of(n / world); }
 
 int nb_sym_create(int n, int world, int rank, nb_sym** out) {
     if (!out || n < 1 || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n % world != 0) return NB_ERR_ARG;
@@ -771,7 +780,7 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur, d
     I.pi = h->d_pi, I.pj = peer_pj[P.rank];
     I.pi_ptr = h->d_tables, I.pi_list = h->d_tables + h->off_pi_list;
     I.pj_ptr = h->d_tables + h->off_pj_ptr, I.pj_list = h->d_tables + h->off_pj_list;
-    I.shard = P.shard, I.i_begin = P.rank * P.shard;
+    I.shard = P.shard, I.i_begin = P.rank * P.shard, I.row_stride = P.row_stride;
     I.fst_next = fst_value(step + 1);
     I.parity = step & 1;
     I.acc_target = P.world > 1 ? (unsigned long long)P.blocks * (h->steps_done[step & 1] + 1) : 0;

@@ -56,6 +56,7 @@ struct Plan {
     int n = 0, world = 1, rank = 0, blocks = 0;
     int shard = 0;       // bodies per rank (n / world)
     int rows_local = 0;  // rows of this rank's shard
+    int row_stride = 0;  // bodies per row (the last one may be shorter): the shard spread evenly over the fewest rows, <= SB
     int rows_global = 0; // rows of all ranks (world * rows_local)
     std::vector<Seg> segs;
     std::vector<int> block_seg_begin;  // [blocks + 1]

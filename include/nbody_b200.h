@@ -274,7 +274,7 @@ int nb_sym_unpack_rows(nb_sym* h, const double* pos4_dev, double* q_own_planar_d
 int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, int* segs_out, int* n_segs,
                          int* block_seg_begin, int* pj_ptr, int* pj_list, int max_pj, long long* sym_pairs,
                          long long* onesided_pairs);
-int nb_sym_row_size(void);         /* bodies per row (= i-bodies per thread block) of this build */
+int nb_sym_row_size(void);         /* largest row (= i-bodies per thread block) of this build */
 int nb_sym_rows(int n, int world); /* rows per rank */
 int nb_sym_row_stride(int n, int world); /* bodies per row: the shard spread evenly over the fewest rows */
 

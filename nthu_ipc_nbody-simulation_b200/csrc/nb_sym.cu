@@ -49,15 +49,15 @@ struct Span {
 // The bodies of a shard are spread EVENLY over the fewest rows that hold them: a row always occupies all SB register slots
 // of its block (a short row leaves lanes idle but takes as long per j body), so rows of equal length keep the cost of a
 // (row, j) unit uniform.  stride = bodies per row.
-int stride_of(int shard) {
-    const int rows = (shard + SB - 1) / SB;
+int stride_of(int shard, int sb) {
+    const int rows = (shard + sb - 1) / sb;
     return (shard + rows - 1) / rows;
 }
-int rows_of(int shard) { return (shard + stride_of(shard) - 1) / stride_of(shard); }
+int rows_of(int shard, int sb) { return (shard + stride_of(shard, sb) - 1) / stride_of(shard, sb); }
 
 // the spans of rank p, phase by phase (phase 0 = local, phase 1 = remote)
-void spans_of_rank(int n, int world, int p, std::vector<std::vector<Span>>& phases) {
-    const int S = n / world, R = rows_of(S), base = p * S, RS = stride_of(S);
+void spans_of_rank(int n, int world, int p, int sb, std::vector<std::vector<Span>>& phases) {
+    const int S = n / world, R = rows_of(S, sb), base = p * S, RS = stride_of(S, sb);
     auto cnt = [&](int r) { return std::min(S, (r + 1) * RS) - r * RS; };
     phases.assign(2, {});
     for (int r = 0; r < R; r++) {
@@ -92,17 +92,31 @@ void spans_of_rank(int n, int world, int p, std::vector<std::vector<Span>>& phas
 }
 }  // namespace
 
-int build_plan(int n, int world, int rank, int blocks, Plan& P) {
+// i-bodies per lane for this shard size: fewest register slots x relative cost of the loop (measured, n = 65536: 2.93 ms
+// with 6 per lane, 3.00 ms with 8)
+int choose_ipl(int n, int world) {
+    static const int forced = getenv("NB_SYM_I") ? atoi(getenv("NB_SYM_I")) : 0;
+    if (forced == IPL_A || forced == IPL_B) return forced;
+    if (n < 1 || world < 1 || n % world) return IPL_A;
+    const int S = n / world;
+    const double ca = (double)rows_of(S, sb_of(IPL_A)) * sb_of(IPL_A) * 1.0, cb = (double)rows_of(S, sb_of(IPL_B)) * sb_of(IPL_B) * 1.025;
+    return cb < ca ? IPL_B : IPL_A;
+}
+
+int build_plan(int n, int world, int rank, int blocks, int ipl, Plan& P) {
     if (n < 1 || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n % world != 0 || blocks < 1) return NB_ERR_ARG;
+    if (ipl != IPL_A && ipl != IPL_B) return NB_ERR_ARG;
     P = Plan{};
+    P.ipl = ipl, P.sb = sb_of(ipl);
+    const int SB = P.sb;
     P.n = n, P.world = world, P.rank = rank, P.blocks = blocks;
     P.shard = n / world;
-    P.rows_local = rows_of(P.shard);
-    P.row_stride = stride_of(P.shard);
+    P.rows_local = rows_of(P.shard, SB);
+    P.row_stride = stride_of(P.shard, SB);
     P.rows_global = world * P.rows_local;
     const int S = P.shard, base = rank * S;
     std::vector<std::vector<Span>> phases;
-    spans_of_rank(n, world, rank, phases);
+    spans_of_rank(n, world, rank, SB, phases);
     std::vector<std::vector<Seg>> per_block(blocks);
     std::vector<double> got(blocks, 0.0);  // cost given to each block so far
     double ideal_before = 0;               // what an exact split of the earlier phases would have given it
@@ -214,7 +228,7 @@ int build_plan(int n, int world, int rank, int blocks, Plan& P) {
     std::vector<std::vector<int>> contrib(P.rows_local);
     for (int p = 0; p < world; p++) {
         std::vector<std::vector<Span>> ph;
-        spans_of_rank(n, world, p, ph);
+        spans_of_rank(n, world, p, SB, ph);
         for (const auto& spans : ph)
             for (const auto& s : spans) {
                 if (s.onesided || s.src != rank) continue;
@@ -325,7 +339,9 @@ __device__ __forceinline__ void pair_sym(double xi, double yi, double zi, double
 
 __device__ __forceinline__ double rot(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+template <int I_PER_LANE>
 __global__ void __launch_bounds__(NT, MIN_BLOCKS) sym_accel_kernel(AccelArgs A, Peers peers) {
+    constexpr int WARP_I = 32 * I_PER_LANE, SB = WARPS * WARP_I;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double4* tile = reinterpret_cast<double4*>(smem_raw);                         // [STAGES][TJ]
     double* stg = reinterpret_cast<double*>(smem_raw + STAGES * TILE_BYTES);      // [2][WARPS][3][TJ]
@@ -477,15 +493,21 @@ struct IntegrateArgs {
     const double* pi;
     const double* pj;  // own PJ
     const int *pi_ptr, *pi_list, *pj_ptr, *pj_list;
-    int shard, i_begin, row_stride;
+    int shard, i_begin, row_stride, sb;
     double fst_next;
     int parity;                     // of this step: partial counters waited on, position counters raised
     unsigned long long acc_target;  // 0 = nothing to wait for (one rank)
     int* status;
 };
 
-// a = sum of the partials in a fixed order; v += a*dt; q += v*dt (nbody.cc:77-88); new pos4 record to every rank
-__global__ void __launch_bounds__(128) sym_integrate_kernel(IntegrateArgs A, Peers peers) {
+// a = sum of the partials in a fixed order; v += a*dt; q += v*dt (nbody.cc:77-88); new pos4 record to every rank.
+// A block takes IB consecutive bodies; the partial rows of a body (PI slots of its row, then the PJ rows the plan lists:
+// up to ~80 at 8 ranks) are dealt round-robin to IP threads, which sum their share in ascending order; the IP shares
+// meet in shared memory and are added in part order - deterministic, and IP times the memory parallelism of one thread
+// per body.
+constexpr int IB = 32, IP = 8;
+__global__ void __launch_bounds__(IB * IP) sym_integrate_kernel(IntegrateArgs A, Peers peers) {
+    __shared__ double part[IP][3][IB];
     if (A.acc_target) {
         if (threadIdx.x < peers.world) {
             const unsigned long long* ctr = peers.counters[peers.my_rank] + (1 * 2 + A.parity) * MAX_PEERS + threadIdx.x;
@@ -499,23 +521,36 @@ __global__ void __launch_bounds__(128) sym_integrate_kernel(IntegrateArgs A, Pee
         }
         __syncthreads();
     }
-    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bx = threadIdx.x % IB, pt = threadIdx.x / IB;
+    const int il = blockIdx.x * IB + bx;
+    double a[3] = {0.0, 0.0, 0.0};
     if (il < A.shard) {
         const int row = il / A.row_stride;
-        double a[3] = {0.0, 0.0, 0.0};
-        for (int s = A.pi_ptr[row]; s < A.pi_ptr[row + 1]; s++) {
-            // {slot, first local body, bodies} of a row run that covers (part of) this aligned row
-            const int idx = il - A.pi_list[3 * s + 1];
-            if (idx >= 0 && idx < A.pi_list[3 * s + 2]) {
-                const double* p = A.pi + (size_t)A.pi_list[3 * s] * 3 * SB + idx;
-                a[0] += p[0], a[1] += p[SB], a[2] += p[2 * SB];
+        const int p0 = A.pi_ptr[row], npi = A.pi_ptr[row + 1] - p0, j0 = A.pj_ptr[row], npj = A.pj_ptr[row + 1] - j0;
+#pragma unroll 2
+        for (int k = pt; k < npi + npj; k += IP) {
+            if (k < npi) {
+                // {slot, first local body, bodies} of a row run that covers (part of) this row
+                const int s = p0 + k, idx = il - A.pi_list[3 * s + 1];
+                if (idx >= 0 && idx < A.pi_list[3 * s + 2]) {
+                    const double* p = A.pi + (size_t)A.pi_list[3 * s] * 3 * A.sb + idx;
+                    a[0] += p[0], a[1] += p[A.sb], a[2] += p[2 * A.sb];
+                }
+            } else {
+                const double* p = A.pj + (size_t)A.pj_list[j0 + k - npi] * 3 * A.shard + il;
+                a[0] += p[0], a[1] += p[A.shard], a[2] += p[2 * (size_t)A.shard];
             }
         }
-        const int e = A.pj_ptr[row + 1];
-#pragma unroll 4
-        for (int s = A.pj_ptr[row]; s < e; s++) {
-            const double* p = A.pj + (size_t)A.pj_list[s] * 3 * A.shard + il;
-            a[0] += p[0], a[1] += p[A.shard], a[2] += p[2 * (size_t)A.shard];
+    }
+    part[pt][0][bx] = a[0], part[pt][1][bx] = a[1], part[pt][2][bx] = a[2];
+    __syncthreads();
+    if (pt == 0 && il < A.shard) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double t = part[0][c][bx];
+#pragma unroll
+            for (int q = 1; q < IP; q++) t += part[q][c][bx];
+            a[c] = t;
         }
         const int i = A.i_begin + il;
         const double4 p = A.pos4[i];
@@ -602,8 +637,12 @@ static int sym_default_blocks(int* out) {
     if (it == cache.end()) {
         int sms = 0, per_sm = 0;
         NB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        NB_CUDA(cudaFuncSetAttribute(sym_accel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sym_accel_kernel, NT, SMEM_BYTES));
+        int per_sm_b = 0;
+        NB_CUDA(cudaFuncSetAttribute(sym_accel_kernel<IPL_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        NB_CUDA(cudaFuncSetAttribute(sym_accel_kernel<IPL_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sym_accel_kernel<IPL_A>, NT, SMEM_BYTES));
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, sym_accel_kernel<IPL_B>, NT, SMEM_BYTES));
+        if (per_sm_b < per_sm) per_sm = per_sm_b;
         if (per_sm < 1) {
             set_error_detail("symmetric kernel does not fit on this GPU");
             return NB_ERR_UNSUPPORTED;
@@ -622,7 +661,7 @@ int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, i
                          int* block_seg_begin, int* pj_ptr, int* pj_list, int max_pj, long long* sym_pairs,
                          long long* onesided_pairs) {
     Plan P;
-    int rc = build_plan(n, world, rank, blocks, P);
+    int rc = build_plan(n, world, rank, blocks, choose_ipl(n, world), P);
     if (rc) return rc;
     if (n_segs) *n_segs = (int)P.segs.size();
     if (sym_pairs) *sym_pairs = P.sym_pairs;
@@ -641,9 +680,11 @@ int nb_sym_plan_describe(int n, int world, int rank, int blocks, int max_segs, i
     return NB_OK;
 }
 
-int nb_sym_row_size(void) { return SB; }
-int nb_sym_rows(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : rows_of(n / world); }
-int nb_sym_row_stride(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : stride_of(n / world); }
+int nb_sym_row_size(void) { return MAX_SB; }
+int nb_sym_rows(int n, int world) { return (n < 1 || world < 1 || n % world) ? 0 : rows_of(n / world, sb_of(choose_ipl(n, world))); }
+int nb_sym_row_stride(int n, int world) {
+    return (n < 1 || world < 1 || n % world) ? 0 : stride_of(n / world, sb_of(choose_ipl(n, world)));
+}
 
 int nb_sym_create(int n, int world, int rank, nb_sym** out) {
     if (!out || n < 1 || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n % world != 0) return NB_ERR_ARG;
@@ -651,14 +692,14 @@ int nb_sym_create(int n, int world, int rank, nb_sym** out) {
     int rc = sym_default_blocks(&blocks);
     if (rc) return rc;
     nb_sym* h = new nb_sym();
-    rc = build_plan(n, world, rank, blocks, h->plan);
+    rc = build_plan(n, world, rank, blocks, choose_ipl(n, world), h->plan);
     if (rc) {
         delete h;
         return rc;
     }
     const Plan& P = h->plan;
     cudaGetDevice(&h->gpu);
-    h->integrate_blocks = (P.shard + 127) / 128;
+    h->integrate_blocks = (P.shard + IB - 1) / IB;
     std::vector<int> tables;
     tables.insert(tables.end(), P.pi_ptr.begin(), P.pi_ptr.end());
     h->off_pi_list = (int)tables.size();
@@ -675,7 +716,7 @@ int nb_sym_create(int n, int world, int rank, nb_sym** out) {
     ok(cudaMalloc(&h->d_segs, std::max<size_t>(1, P.segs.size()) * sizeof(Seg)));
     ok(cudaMalloc(&h->d_bsb, (blocks + 1) * sizeof(int)));
     ok(cudaMalloc(&h->d_tables, tables.size() * sizeof(int)));
-    ok(cudaMalloc(&h->d_pi, std::max<size_t>(1, (size_t)P.pi_slots) * 3 * SB * sizeof(double)));
+    ok(cudaMalloc(&h->d_pi, std::max<size_t>(1, (size_t)P.pi_slots) * 3 * P.sb * sizeof(double)));
     if (e == cudaSuccess && !P.segs.empty())
         ok(cudaMemcpy(h->d_segs, P.segs.data(), P.segs.size() * sizeof(Seg), cudaMemcpyHostToDevice));
     if (e == cudaSuccess) ok(cudaMemcpy(h->d_bsb, P.block_seg_begin.data(), (blocks + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -765,7 +806,10 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur, d
             NB_CUDA(cudaEventCreate(&pe1));
             NB_CUDA(cudaEventRecord(pe0, st));
         }
-        sym_accel_kernel<<<P.blocks, NT, SMEM_BYTES, st>>>(A, peers);
+        if (P.ipl == IPL_B)
+            sym_accel_kernel<IPL_B><<<P.blocks, NT, SMEM_BYTES, st>>>(A, peers);
+        else
+            sym_accel_kernel<IPL_A><<<P.blocks, NT, SMEM_BYTES, st>>>(A, peers);
         count_launch();
         NB_CUDA(cudaGetLastError());
         if (prof) {
@@ -780,12 +824,12 @@ int nb_sym_step_phase(nb_sym* h, int step, int phases, const double* pos4_cur, d
     I.pi = h->d_pi, I.pj = peer_pj[P.rank];
     I.pi_ptr = h->d_tables, I.pi_list = h->d_tables + h->off_pi_list;
     I.pj_ptr = h->d_tables + h->off_pj_ptr, I.pj_list = h->d_tables + h->off_pj_list;
-    I.shard = P.shard, I.i_begin = P.rank * P.shard, I.row_stride = P.row_stride;
+    I.shard = P.shard, I.i_begin = P.rank * P.shard, I.row_stride = P.row_stride, I.sb = P.sb;
     I.fst_next = fst_value(step + 1);
     I.parity = step & 1;
     I.acc_target = P.world > 1 ? (unsigned long long)P.blocks * (h->steps_done[step & 1] + 1) : 0;
     I.status = status_dev;
-    sym_integrate_kernel<<<h->integrate_blocks, 128, 0, st>>>(I, peers);
+    sym_integrate_kernel<<<h->integrate_blocks, IB * IP, 0, st>>>(I, peers);
     count_launch();
     NB_CUDA(cudaGetLastError());
     h->steps_done[step & 1]++;
@@ -810,7 +854,7 @@ int nb_sym_publish_rows(nb_sym* h, int step_next, const double* q_own_planar_dev
         peers.counters[p] = P.world > 1 ? peer_counters[p] : nullptr;
     }
     const int par = (step_next - 1) & 1;  // the parity the coming step's acceleration kernel waits on
-    sym_publish_kernel<<<h->integrate_blocks, 128, 0, (cudaStream_t)stream>>>(q_own_planar_dev, m0_dev, is_device_dev, P.shard,
+    sym_publish_kernel<<<h->integrate_blocks, IB, 0, (cudaStream_t)stream>>>(q_own_planar_dev, m0_dev, is_device_dev, P.shard,
                                                                             P.rank * P.shard, fst_value(step_next), par, peers);
     count_launch();
     NB_CUDA(cudaGetLastError());

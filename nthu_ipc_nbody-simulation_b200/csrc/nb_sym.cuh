@@ -11,9 +11,6 @@ namespace sym {
 // n = 65536 (profiles/r02_sym_variants.md): 6 i-bodies per lane, 8 warps, ONE block per SM (254 registers: the six pair
 // chains of a rotation interleave instruction by instruction) 2.93 ms/step; 4 per lane at 128 registers, 16 warps/SM
 // (chains serialised by the register budget, 8-cycle dependent stalls) 3.28 ms; 12 warps x 168 registers 3.12 ms.
-#ifndef NB_SYM_I
-#define NB_SYM_I 6
-#endif
 #ifndef NB_SYM_WARPS
 #define NB_SYM_WARPS 8
 #endif
@@ -23,11 +20,14 @@ namespace sym {
 #ifndef NB_SYM_TJ
 #define NB_SYM_TJ 128
 #endif
-constexpr int I_PER_LANE = NB_SYM_I;     // i-bodies per lane
-constexpr int WARP_I = 32 * I_PER_LANE;  // i-bodies per warp
 constexpr int WARPS = NB_SYM_WARPS;      // warps per block
 constexpr int MIN_BLOCKS = NB_SYM_MIN_BLOCKS;  // resident blocks per SM the register budget is set for
-constexpr int SB = WARPS * WARP_I;       // bodies per row (superblock) = i-bodies per block
+// i-bodies per lane: two instantiations of the kernel.  6 (rows of up to 1536 bodies) is the faster loop; 8 (2048) wastes no
+// register slots when the shard is a power of two (8192 bodies per rank at 8 ranks = 4 rows of 2048, against 6 rows of
+// 1366 in 1536 slots).  choose_ipl() takes the one with the smaller slots x cost product; NB_SYM_I overrides.
+constexpr int IPL_A = 6, IPL_B = 8;
+constexpr int sb_of(int ipl) { return WARPS * 32 * ipl; }  // bodies per row (superblock) = i-bodies per block
+constexpr int MAX_SB = sb_of(IPL_B);
 constexpr int TJ = NB_SYM_TJ;            // j bodies per shared-memory tile
 constexpr int STAGES = 3;                // TMA ring depth
 constexpr int SUB = 32;                  // scheduling granularity along j (one warp rotation group)
@@ -55,6 +55,7 @@ struct Seg {
 struct Plan {
     int n = 0, world = 1, rank = 0, blocks = 0;
     int shard = 0;       // bodies per rank (n / world)
+    int ipl = IPL_A, sb = sb_of(IPL_A);  // i-bodies per lane of the kernel instantiation, register slots per row
     int rows_local = 0;  // rows of this rank's shard
     int row_stride = 0;  // bodies per row (the last one may be shorter): the shard spread evenly over the fewest rows, <= SB
     int rows_global = 0; // rows of all ranks (world * rows_local)
@@ -68,7 +69,8 @@ struct Plan {
 };
 
 // Builds the plan of `rank`.  n % world == 0.  Pure host code (no CUDA): tests call it through nb_sym_plan_describe.
-int build_plan(int n, int world, int rank, int blocks, Plan& out);
+int build_plan(int n, int world, int rank, int blocks, int ipl, Plan& out);
+int choose_ipl(int n, int world);
 
 }  // namespace sym
 }  // namespace nb

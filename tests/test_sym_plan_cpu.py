@@ -66,7 +66,7 @@ def test_plan_runs_and_slots(nb):
         assert sorted(slots) == list(range(len(slots))), "every row run has its own PI slot"
 
 
-@pytest.mark.parametrize("n,world,blocks", [(65536, 1, 296), (65536, 2, 296), (65536, 4, 296), (65536, 8, 296), (65536, 8, 148)])
+@pytest.mark.parametrize("n,world,blocks", [(65536, 1, 296), (65536, 2, 296), (65536, 4, 296), (65536, 8, 148), (65536, 4, 148)])
 def test_plan_is_balanced(nb, n, world, blocks):
     worst_rank = []
     for r in range(world):

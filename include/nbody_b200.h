@@ -267,6 +267,13 @@ int nb_sym_publish_rows(nb_sym* h, int step_next, const double* q_own_planar_dev
                         unsigned long long* const* peer_counters, const double* m0_dev,
                         const unsigned char* is_device_dev, void* stream);
 int nb_sym_unpack_rows(nb_sym* h, const double* pos4_dev, double* q_own_planar_dev, void* stream);
+/* the whole host-buffer step in one call: q_own_host / v_own_host are (pinned) planar [3][n/world] host arrays with this
+ * rank's state, in/out; q_own_stage_dev is a device scratch of the same size; peer_pos4_cur / peer_pos4_next are the
+ * buffers the step reads / writes.  Returns when the new state is in the host arrays. */
+int nb_sym_step_host(nb_sym* h, int step, double* q_own_host, double* v_own_host, double* q_own_stage_dev,
+                     const double* pos4_cur_dev, double* const* peer_pos4_cur, double* const* peer_pos4_next,
+                     double* const* peer_pj, unsigned long long* const* peer_counters, int* status_dev,
+                     double* vel_dev, const double* m0_dev, const unsigned char* is_device_dev, void* stream);
 /* The static schedule of one rank (host only, no GPU needed): segments of eight ints
  * {row_body0, row_count, j0, j1, flags, pi_slot, pj_row, src_rank} (flags: 1 = one-sided, 2 = load row, 4 = flush row),
  * block b owns segments [block_seg_begin[b], block_seg_begin[b+1]); pj_ptr / pj_list = per local row the PJ rows

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "nb_large_scratch_bytes", "nb_large_pack", "nb_large_unpack", "nb_large_step", "nb_large_step_p2p", "nb_large_blocks_per_step", "nb_large_p2p_counter_bytes", "nb_large_wait_p2p",
     "nb_dev_alloc", "nb_dev_free", "nb_dev_copy", "nb_ipc_export", "nb_ipc_open", "nb_ipc_close", "nb_fp64_peak", "nb_fp64_peak_variant",
     "nb_sym_create", "nb_sym_destroy", "nb_sym_pj_bytes", "nb_sym_counter_bytes", "nb_sym_blocks", "nb_sym_remote_partial_bytes",
-    "nb_sym_pairs", "nb_sym_wait_positions", "nb_sym_step", "nb_sym_step_phase", "nb_sym_plan_describe", "nb_sym_rows", "nb_sym_row_size", "nb_sym_row_stride", "nb_device_warm", "nb_hw5_narrow_visible_gpus", "nb_sym_publish_rows", "nb_sym_unpack_rows",
+    "nb_sym_pairs", "nb_sym_wait_positions", "nb_sym_step", "nb_sym_step_phase", "nb_sym_plan_describe", "nb_sym_rows", "nb_sym_row_size", "nb_sym_row_stride", "nb_device_warm", "nb_hw5_narrow_visible_gpus", "nb_sym_publish_rows", "nb_sym_unpack_rows", "nb_sym_step_host",
 ]
 
 class _Missing:
@@ -172,6 +172,9 @@ def lib():
     L.nb_sym_publish_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.nb_sym_unpack_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.nb_sym_step_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
     L.nb_sym_plan_describe.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip, C.c_int,
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.nb_sym_rows.argtypes = [C.c_int, C.c_int]

@@ -872,6 +872,32 @@ int nb_sym_unpack_rows(nb_sym* h, const double* pos4_dev, double* q_own_planar_d
     return NB_OK;
 }
 
+// run_step with HOST buffers in one call (bench e2e, nbody.cc:51-54 signature, sharded): this rank's positions and
+// velocities (pinned host memory, planar [3][n/world]) go host -> device, are published to every rank, the step's two
+// kernels run, the new rows are extracted and copied device -> host; returns when they are there.
+int nb_sym_step_host(nb_sym* h, int step, double* q_own_host, double* v_own_host, double* q_own_stage_dev,
+                     const double* pos4_cur, double* const* peer_pos4_cur, double* const* peer_pos4_next,
+                     double* const* peer_pj, unsigned long long* const* peer_counters, int* status_dev, double* vel_dev,
+                     const double* m0_dev, const unsigned char* is_device_dev, void* stream) {
+    if (!h || !q_own_host || !v_own_host || !q_own_stage_dev || !peer_pos4_cur || !peer_pos4_next) return NB_ERR_ARG;
+    const size_t bytes = 3 * (size_t)h->plan.shard * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    NB_CUDA(cudaMemcpyAsync(q_own_stage_dev, q_own_host, bytes, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(vel_dev, v_own_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = nb_sym_publish_rows(h, step, q_own_stage_dev, peer_pos4_cur, peer_counters, m0_dev, is_device_dev, stream);
+    if (rc) return rc;
+    rc = nb_sym_step_phase(h, step, 3, pos4_cur, peer_pos4_next, peer_pj, peer_counters, status_dev, vel_dev, m0_dev, is_device_dev,
+                           stream);
+    if (rc) return rc;
+    // the rank's own rows of the next buffer were written by its own integrate kernel: stream order suffices
+    rc = nb_sym_unpack_rows(h, peer_pos4_next[h->plan.rank], q_own_stage_dev, stream);
+    if (rc) return rc;
+    NB_CUDA(cudaMemcpyAsync(q_own_host, q_own_stage_dev, bytes, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(v_own_host, vel_dev, bytes, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    return NB_OK;
+}
+
 int nb_sym_step(nb_sym* h, int step, const double* pos4_cur, double* const* peer_pos4_next, double* const* peer_pj,
                 unsigned long long* const* peer_counters, int* status_dev, double* vel_dev, const double* m0_dev,
                 const unsigned char* is_device_dev, void* stream) {

@@ -345,17 +345,14 @@ class SymShardedSystem:
         if not hasattr(self, "_q_own"):
             self._q_own = torch.empty(3 * self.i_count, dtype=torch.float64, device=self.device)
         st = torch.cuda.current_stream().cuda_stream
-        self._q_own.copy_(q_own_host.view(-1), non_blocking=True)
-        self.vel.copy_(v_own_host, non_blocking=True)
-        _check(L.nb_sym_publish_rows(self.h, self.step + 1, C.c_void_p(self._q_own.data_ptr()), self.peer_pos[self.cur],
-                                     self.peer_ctr, C.c_void_p(self.m0.data_ptr()), C.c_void_p(self.isdev.data_ptr()),
-                                     C.c_void_p(st)))
-        self.step_phase(3)
-        # the rank's own rows of the new buffer were written by its own integrate kernel: stream order suffices
-        _check(L.nb_sym_unpack_rows(self.h, C.c_void_p(self.own[self.cur]), C.c_void_p(self._q_own.data_ptr()), C.c_void_p(st)))
-        q_own_host.view(-1).copy_(self._q_own, non_blocking=True)
-        v_own_host.copy_(self.vel, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        step = self.step + 1
+        _check(L.nb_sym_step_host(self.h, step, C.c_void_p(q_own_host.data_ptr()), C.c_void_p(v_own_host.data_ptr()),
+                                  C.c_void_p(self._q_own.data_ptr()), C.c_void_p(self.own[self.cur]), self.peer_pos[self.cur],
+                                  self.peer_pos[self.cur ^ 1], self.peer_pj, self.peer_ctr,
+                                  C.c_void_p(self.own[3] + self.ctr_bytes), C.c_void_p(self.vel.data_ptr()),
+                                  C.c_void_p(self.m0.data_ptr()), C.c_void_p(self.isdev.data_ptr()), C.c_void_p(st)))
+        self.step = step
+        self.cur ^= 1
         nbytes = (q_own_host.numel() + v_own_host.numel()) * 8
         return nbytes, nbytes
 

@@ -439,6 +439,49 @@ def test_ensemble_members_match_individual_runs(nb, oracle):
     assert not np.array_equal(q[1], q[2])
 
 
+def test_symmetric_single_block_kernel_b1024_ensemble(nb, oracle, kats):
+    """The 1024-body ensemble (config C4) runs on traj_sym_kernel (every unordered pair of different groups once).
+    (1) the four trajectories of b1024 (query 1, query 2, query 3 for both devices) as ONE ensemble launch, full
+    200 000 steps: events equal the oracle's known answers and the golden; (2) state after 2000 steps against the CPU
+    oracle at the FAST tolerance (q within 2 ulp); (3) a 900-body system (partial last group) against the oracle."""
+    s = nb.read_input(case_path("b1024"))
+    devs = s.devices
+    # (2) + resume in two launches
+    S = 2
+    q, v = np.tile(s.q, (S, 1)), np.tile(s.v, (S, 1))
+    m, dev = np.tile(s.m, (S, 1)), np.tile(s.is_device, (S, 1))
+    ev, _ = nb.ensemble_run(q, v, m, dev, [s.planet] * S, [s.asteroid] * S, kind=nb.KIND_Q2, step_end=2000)
+    qo, vo = s.q.copy(), s.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, s.n, qo, vo, s.m, s.is_device, 0, 2000)
+    assert ulps(q[0], qo).max() <= 2 and np.allclose(v[0], vo, rtol=1e-12, atol=0)
+    assert np.array_equal(q[0], q[1]) and ev[0].steps_done == 2000
+    # (3) ragged
+    r = nb.synthetic_system(900, seed=5)
+    q, v = r.q.copy()[None], r.v.copy()[None]
+    nb.ensemble_run(q, v, r.m[None], r.is_device[None], [0], [1], kind=nb.KIND_PLAIN, step_end=50)
+    qo, vo = r.q.copy(), r.v.copy()
+    oracle.run_steps(oracle.MODE_SQRT3, r.n, qo, vo, r.m, r.is_device, 0, 50)
+    assert ulps(q[0], qo).max() <= 2 and np.allclose(v[0], vo, rtol=1e-12, atol=0)
+    # (1) full length, one launch for each kind (kinds are per launch)
+    k = kats["b1024"]
+    g = golden_lines("b1024")
+    one = lambda a: a.copy()[None]
+    e1, _ = nb.ensemble_run(one(s.q), one(s.v), one(np.where(s.is_device, 0.0, s.m)), one(s.is_device), [s.planet], [s.asteroid],
+                            kind=nb.KIND_Q1, step_end=nb.N_STEPS)
+    assert e1[0].argmin_step == k["argmin_step"] and abs(np.sqrt(e1[0].min_d2) - g["min_dist"]) <= MIN_DIST_RTOL * g["min_dist"]
+    e2, _ = nb.ensemble_run(one(s.q), one(s.v), one(s.m), one(s.is_device), [s.planet], [s.asteroid], kind=nb.KIND_Q2,
+                            step_end=nb.N_STEPS)
+    assert e2[0].hit_step == g["hit_time_step"]
+    assert list(e2[0].reach_step[:len(devs)]) == [d["reach_step"] for d in k["devices"]]
+    S = len(devs)
+    e3, _ = nb.ensemble_run(np.tile(s.q, (S, 1)), np.tile(s.v, (S, 1)), np.tile(s.m, (S, 1)), np.tile(s.is_device, (S, 1)),
+                            [s.planet] * S, [s.asteroid] * S, kind=nb.KIND_Q3, destroy_device=devs, step_end=nb.N_STEPS)
+    for i, d in enumerate(k["devices"]):
+        assert e3[i].hit_step == d["q3_hit_step"] and e3[i].destroyed_step == d["reach_step"]
+    saved = [(e3[i].cost, devs[i]) for i in range(S) if e3[i].hit_step == -2]
+    assert min(saved)[1] == g["gravity_device_id"] and min(saved)[0] == g["missile_cost"]
+
+
 # ---- large-N path ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1025, 3000, 4096])
 def test_large_path_strict_bitwise(nb, oracle, n):

@@ -190,10 +190,11 @@ traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst) 
 //   * group pairs (w, w+1), (w, w+2), (w, w+3) (mod 8) are warp w's, symmetric: the 128 j bodies of the other group pass
 //     through the warp 32 at a time, one per lane, rotating through the lanes by warp shuffles with their own
 //     acceleration accumulators; what a j body has collected is left in shared memory for its owner;
-//   * the warp's own group (w, w) and the opposite group (w, w+4) are evaluated one-sided (ordered pairs, broadcast reads);
+//   * the warp's own group (w, w) is evaluated one-sided (ordered pairs, broadcast reads); the opposite group (w, w+4)
+//     is shared half and half with its owner, symmetric too;
 //   * after one block barrier every lane adds the three partial sums other warps left for its bodies (fixed order:
 //     deterministic), integrates (nbody.cc:77-88) and writes the new record; observers as in traj_kernel.
-// FP64 instructions per body-step: 128*16 + 3*128*20 + 128*16 = 92 per j group against 8*16 = 128 for the one-sided kernel.
+// FP64 instructions per body-step: 128*16 + 3*128*20 + 64*20 = 86 per j group against 8*16 = 128 for the one-sided kernel.
 constexpr int TS_WARPS = 8, TS_G = 128, TS_I = 4;
 
 __device__ __forceinline__ void ts_pair_sym(double xi, double yi, double zi, double gmi, double xj, double yj, double zj, double gmj,
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(32 * TS_WARPS, 1)
 traj_sym_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst) {
     extern __shared__ __align__(32) unsigned char ts_smem[];
     double4* pos = reinterpret_cast<double4*>(ts_smem);                                   // [2][1024] {x, y, z, G*m_eff}
-    double* stg = reinterpret_cast<double*>(ts_smem + 2 * 1024 * sizeof(double4));        // [8 warps][3 targets][3][128]
+    double* stg = reinterpret_cast<double*>(ts_smem + 2 * 1024 * sizeof(double4));        // [8 warps][4 targets][3][128]
     const TrajDesc d = descs[blockIdx.x];
     const int n = d.n;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -302,10 +303,9 @@ traj_sym_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ f
             xi[k] = p.x, yi[k] = p.y, zi[k] = p.z, gi[k] = p.w;
             ax[k] = ay[k] = az[k] = 0.0;
         }
-        // (2a) own group and opposite group, one-sided: every lane reads the same j record; the self term is exactly zero
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            const double4* gj = cp + TS_G * ((w + 4 * half) & 7);
+        // (2a) own group, one-sided: every lane reads the same j record; the self term is exactly zero
+        {
+            const double4* gj = cp + TS_G * w;
 #pragma unroll 2
             for (int j = 0; j < TS_G; j++) {
                 const double4 b = gj[j];
@@ -316,13 +316,37 @@ traj_sym_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ f
                 for (int k = 0; k < TS_I; k++) pair_accum_fast(c[k], dx[k], dy[k], dz[k], ax[k], ay[k], az[k]);
             }
         }
-        // (2b) groups w+1, w+2, w+3: symmetric, the j bodies rotate through the lanes
+        // (2b) groups w+1, w+2, w+3: symmetric, the j bodies rotate through the lanes.  The opposite group w+4 is shared
+        //      with its owner: warps 0..3 take the first 64 bodies of it against all their own, warps 4..7 take all 128
+        //      bodies of it against the second 64 of their own (register slots 2 and 3) - together every pair once.
 #pragma unroll 1
-        for (int dg = 1; dg <= 3; dg++) {
+        for (int dg = 1; dg <= 4; dg++) {
             const double4* gj = cp + TS_G * ((w + dg) & 7);
-            double* out = stg + ((w * 3 + (dg - 1)) * 3) * TS_G;
+            double* out = stg + ((w * 4 + (dg - 1)) * 3) * TS_G;
+            const int jn = (dg == 4 && w < 4) ? TS_G / 2 : TS_G;
+            if (dg == 4 && w >= 4) {
 #pragma unroll 1
-            for (int s0 = 0; s0 < TS_G; s0 += 32) {
+                for (int s0 = 0; s0 < TS_G; s0 += 32) {
+                    const double4 b = gj[s0 + lane];
+                    double jx = b.x, jy = b.y, jz = b.z, jg = b.w;
+                    double ajx = 0.0, ajy = 0.0, ajz = 0.0;
+#pragma unroll 4
+                    for (int r = 0; r < 32; r++) {
+                        const double nx = __shfl_sync(0xffffffffu, jx, src_lane), ny = __shfl_sync(0xffffffffu, jy, src_lane),
+                                     nz = __shfl_sync(0xffffffffu, jz, src_lane), ng = __shfl_sync(0xffffffffu, jg, src_lane);
+#pragma unroll
+                        for (int k = TS_I / 2; k < TS_I; k++)
+                            ts_pair_sym(xi[k], yi[k], zi[k], gi[k], jx, jy, jz, jg, ax[k], ay[k], az[k], ajx, ajy, ajz);
+                        ajx = __shfl_sync(0xffffffffu, ajx, src_lane), ajy = __shfl_sync(0xffffffffu, ajy, src_lane),
+                        ajz = __shfl_sync(0xffffffffu, ajz, src_lane);
+                        jx = nx, jy = ny, jz = nz, jg = ng;
+                    }
+                    out[s0 + lane] = ajx, out[TS_G + s0 + lane] = ajy, out[2 * TS_G + s0 + lane] = ajz;
+                }
+                continue;
+            }
+#pragma unroll 1
+            for (int s0 = 0; s0 < jn; s0 += 32) {
                 const double4 b = gj[s0 + lane];
                 double jx = b.x, jy = b.y, jz = b.z, jg = b.w;
                 double ajx = 0.0, ajy = 0.0, ajz = 0.0;
@@ -348,8 +372,10 @@ traj_sym_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ f
             const int off = 32 * k + lane;
             double a0 = ax[k], a1 = ay[k], a2 = az[k];
 #pragma unroll
-            for (int dg = 1; dg <= 3; dg++) {
-                const double* in = stg + ((((w - dg) & 7) * 3 + (dg - 1)) * 3) * TS_G;
+            for (int dg = 1; dg <= 4; dg++) {
+                // the opposite warp (dg == 4): warps 0..3 left sums for the first 64 bodies of this group only
+                if (dg == 4 && w >= 4 && k >= TS_I / 2) continue;
+                const double* in = stg + ((((w - dg) & 7) * 4 + (dg - 1)) * 3) * TS_G;
                 a0 += in[off], a1 += in[TS_G + off], a2 += in[2 * TS_G + off];
             }
             double x = xi[k], y = yi[k], z = zi[k];
@@ -388,7 +414,7 @@ traj_sym_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ f
 }
 
 int launch_sym(int n_traj, const TrajDesc* descs, const double* fst, cudaStream_t stream) {
-    const size_t smem = 2 * 1024 * sizeof(double4) + (size_t)TS_WARPS * 3 * 3 * TS_G * sizeof(double);
+    const size_t smem = 2 * 1024 * sizeof(double4) + (size_t)TS_WARPS * 4 * 3 * TS_G * sizeof(double);
     NB_CUDA(cudaFuncSetAttribute(traj_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     traj_sym_kernel<<<n_traj, 32 * TS_WARPS, smem, stream>>>(descs, fst);
     count_launch();

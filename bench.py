@@ -544,6 +544,15 @@ def run_ours(args):
                  "trajectories": ans.n_trajectories, "matches_golden": bool(ok), "line1_byte_identical": tl[0] == gl[0],
                  "us_per_step_q1": None,
                  "note": "in-process solve (contexts already created); as many GPUs as trajectories: Q1, Q2 and one Q3 trajectory per device from step 0, one per rank; fewer: Q1 on rank 0, Q2 -> Q3 candidates forked from Q2 on rank 1 (chain plan, nb_host.cu)"}
+        if rank == 0:
+            # step latency of ONE system spread over the GPU (the quantity that bounds the >= 4-GPU solve): query 1, all steps
+            tr = nb.Trajectory(s1024, nb.KIND_Q1, gpu=local)
+            tr.run(2000)
+            tq = time.perf_counter()
+            tr.run(nb.N_STEPS)
+            b1024["us_per_step_q1"] = (time.perf_counter() - tq) / (nb.N_STEPS - 2000) * 1e6
+            tr.close()
+            b1024["torn_records_detected"] = nb.grid_torn_records()
         if rank == 0 and not args.no_hw5_process:
             b1024["hw5_process"] = hw5_process_block(nb)
         barrier()

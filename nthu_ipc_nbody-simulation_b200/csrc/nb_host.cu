@@ -250,10 +250,15 @@ struct DeviceBatch {
         if (grid) NB_CUDA(cudaMemcpyAsync(pin_status, grid_traj_status(grid_ws, n), 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         // Busy-wait instead of cudaStreamSynchronize: the blocking wait costs tens of milliseconds of wake-up latency now
         // and then (measured on the B200 boxes), and the chain plan of nb_solve comes through here every few thousand steps.
+        // (round 2: spin for the first 200 us only, then poll every 20 us - a launch lasts milliseconds to seconds, and
+        // a host core at 100 % for all of it bought nothing)
+        const auto w0 = std::chrono::steady_clock::now();
         for (;;) {
             cudaError_t qe = cudaStreamQuery(stream);
             if (qe == cudaSuccess) break;
             if (qe != cudaErrorNotReady) return cuda_fail(qe, "cudaStreamQuery", __FILE__, __LINE__);
+            if (std::chrono::steady_clock::now() - w0 > std::chrono::microseconds(200))
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         memcpy(h_ev.data(), pin_ev, S * sizeof(nb_events));
         if (pin_status[1] != 0) g_torn_records += pin_status[1];  // records that failed the full self-check and were fetched again

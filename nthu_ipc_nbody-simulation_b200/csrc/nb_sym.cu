@@ -27,9 +27,6 @@
 #include "nb_math.cuh"
 #include "nb_sym.cuh"
 
-#ifndef NB_SYM_EXP
-#define NB_SYM_EXP 0
-#endif
 #ifndef NB_SYM_UNROLL
 #define NB_SYM_UNROLL 2
 #endif
@@ -328,13 +325,9 @@ __device__ __forceinline__ void pair_sym(double xi, double yi, double zi, double
     aix = fma(ci, dx, aix);
     aiy = fma(ci, dy, aiy);
     aiz = fma(ci, dz, aiz);
-#if NB_SYM_EXP != 2  // timing experiment 2: without the a_j side (wrong results)
     ajx = fma(-cj, dx, ajx);
     ajy = fma(-cj, dy, ajy);
     ajz = fma(-cj, dz, ajz);
-#else
-    ajx += cj;
-#endif
 }
 
 __device__ __forceinline__ double rot(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -443,9 +436,7 @@ __global__ void __launch_bounds__(NT, MIN_BLOCKS) sym_accel_kernel(AccelArgs A, 
 #pragma unroll
                         for (int k = 0; k < I_PER_LANE; k++)
                             pair_sym(xi[k], yi[k], zi[k], gi[k], jx, jy, jz, jg, ax[k], ay[k], az[k], ajx, ajy, ajz);
-#if NB_SYM_EXP != 1  // timing experiment 1: accumulators stay (wrong results)
                         ajx = rot(ajx, src_lane), ajy = rot(ajy, src_lane), ajz = rot(ajz, src_lane);
-#endif
                         jx = nx, jy = ny, jz = nz, jg = ng;
                     }
                     if (jl < cnt) my_stg[jl] = ajx, my_stg[TJ + jl] = ajy, my_stg[2 * TJ + jl] = ajz;

@@ -169,6 +169,8 @@ struct Shared {
     volatile int flags[MAX_T][2];   // FLAG_* of the step held by the stage, valid once obs completed
     volatile int stop[MAX_T];
     volatile int abort;
+    volatile int delay[MAX_T];      // copy delay after the trigger (clk): a constant, or steered by stale_own (adaptive mode)
+    volatile int stale_own[MAX_T];  // this step's validation found stale records in the slice this block's producer copied
     double part[2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part
 };
 
@@ -191,7 +193,7 @@ struct ObsState {  // per system, observer warp
 #define NB_GRID_VALIDATE_ATTR __forceinline__
 #endif
 __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* grec, int R, int st, int tid, int hsel, volatile int* abort_flag,
-                                            int* status, unsigned long long* n_stale) {
+                                            int* status, unsigned long long* n_stale, int own_lo, int own_hi, volatile int* stale_own) {
     bool patched = false;
     double2 va[4], vb[4];  // whole records, conflict-free LDS.128 pairs (lanes with bit 2 set read the second half first)
 #pragma unroll
@@ -222,6 +224,7 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
             pos[4 * r + 3] = tg;
             patched = true;
             (*n_stale)++;
+            if (r >= own_lo && r < own_hi) *stale_own = 1;
         }
     }
     return patched;
@@ -231,7 +234,8 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
 template <int MATH, int T, int NJ, bool PROFILE>
 __global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
-                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single) {
+                 long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single, int adapt_up,
+                 int adapt_down) {
     extern __shared__ __align__(128) double smem[];
     __shared__ Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -256,6 +260,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         for (int t = 0; t < T; t++) {
             // a trajectory that stopped in an earlier launch never steps again
             sh.stop[t] = (descs[t].kind >= NB_KIND_Q2 && descs[t].ev->hit_step != -2) ? 1 : 0;
+            sh.delay[t] = delay_clk;
+            sh.stale_own[t] = 0;
             for (int b = 0; b < 2; b++) {
                 mbar_init(&sh.full[t][b], 1);
                 mbar_init(&sh.obs[t][b], 1);
@@ -374,8 +380,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     // Copy delay after the trigger: long enough for everybody's sectors of this step to be in the L2 when the
                     // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
                     // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
-                    int dl = delay_clk;
-                    if (T > 1) {  // the only system still running in this launch waits for every copy: shortest delay
+                    int dl = adapt_up > 0 ? sh.delay[t] : delay_clk;
+                    if (T > 1 && adapt_up <= 0) {  // the only system still running in this launch waits for every copy: shortest delay
                         int n_act = 0;
 #pragma unroll
                         for (int u = 0; u < T; u++) n_act += pact[u] ? 1 : 0;
@@ -566,10 +572,25 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     //     n = 1024).  A stale record was copied
                     //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
                     //     memory and patch shared memory, each stale record by exactly one thread of the block.
-                    const bool patched = validate_stage(pos, grec, R, st, tid, hsel, &sh.abort, status, &n_stale);
+                    const int own_lo = (int)cluster_ctarank() * (R / (int)cluster_nctarank());
+                    const bool patched = validate_stage(pos, grec, R, st, tid, hsel, &sh.abort, status, &n_stale, own_lo,
+                                                        own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
                     // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
                     if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     compute_bar<32 * NCW>();
+                    if (adapt_up > 0 && tid == 0) {
+                        // closed loop on the copy delay: stale records in the slice this block's producer copied = it copied
+                        // too early (raise the delay by adapt_up); a clean step lowers it by adapt_down.  The slowest
+                        // block never sees stale records, so ITS delay - the one on the critical path - decays to the floor.
+                        int dcur = sh.delay[t];
+                        if (sh.stale_own[t]) {
+                            dcur = min(dcur + adapt_up, 1600);
+                            sh.stale_own[t] = 0;
+                        } else {
+                            dcur = max(dcur - adapt_down, 0);
+                        }
+                        sh.delay[t] = dcur;
+                    }
                 }
                 tick(5);
                 for (int attempt = 0; attempt < 2; attempt++) {
@@ -796,7 +817,18 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         }
     }
     const auto h0 = std::chrono::steady_clock::now();
-    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single));
+    // NB_GRID_ADAPT="up,down" (clk): closed loop on the copy delay, default 128,8; "0,0" = the constant NB_GRID_DELAY.
+    // Measured on B200, b1024, us per step (profiles/r02_grid_exchange.md): constant 900 -> 3.51, constant 400 -> 4.14;
+    // adaptive 128,8 -> 3.47 from either start value (64,8: 3.49; 32,4: 3.53; 200,2: 3.59; 64,32: 3.71): the constant that
+    // had to be tuned per box (round 1: "on another box 750 gave 3.9") is gone, the gain itself is 1 %.
+    static int adapt_up = 128, adapt_down = 8;
+    static const bool adapt_read = [] {
+        const char* e = getenv("NB_GRID_ADAPT");
+        if (e) sscanf(e, "%d,%d", &adapt_up, &adapt_down);
+        return true;
+    }();
+    (void)adapt_read;
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single, adapt_up, adapt_down));
     count_launch();
     {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();

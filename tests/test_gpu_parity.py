@@ -339,7 +339,8 @@ def test_grid_exchange_knobs_never_change_results_full_length(nb):
     results = {}
     for name, knobs in (("default", {}), ("cs1", dict(NB_GRID_CS="1")), ("cs2_t1", dict(NB_GRID_CS="2", NB_GRID_T="1")),
                         ("cs4_delay0", dict(NB_GRID_CS="4", NB_GRID_DELAY="0")), ("cs2_delay0_t2", dict(NB_GRID_CS="2", NB_GRID_DELAY="0", NB_GRID_T="2")),
-                        ("delay5000", dict(NB_GRID_DELAY="5000"))):
+                        ("delay5000_constant", dict(NB_GRID_DELAY="5000", NB_GRID_ADAPT="0,0")), ("constant900", dict(NB_GRID_ADAPT="0,0")),
+                        ("adapt_fast", dict(NB_GRID_ADAPT="400,100"))):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, **knobs), timeout=900)
         assert r.returncode == 0, (name, r.stderr.decode()[-2000:])
         results[name] = json.loads(r.stdout.decode().strip().split("\n")[-1])

@@ -135,8 +135,9 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
 }
+// named barrier of one system's compute warps (id 1 + its warp-set index)
 template <int NTHREADS>
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+__device__ __forceinline__ void compute_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory"); }
 
 // Record layout: one 32-byte sector {x, y, z, tag}.  The tag is SELF-CHECKING: step in the upper 32 bits, a 32-bit
 // fold of the bit patterns of x, y and z in the lower 32, so a record is accepted only if all four words belong
@@ -171,7 +172,7 @@ struct Shared {
     volatile int abort;
     volatile int delay[MAX_T];      // copy delay after the trigger (clk): a constant, or steered by stale_own (adaptive mode)
     volatile int stale_own[MAX_T];  // this step's validation found stale records in the slice this block's producer copied
-    double part[2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part
+    double part[MAX_T][2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part ([0] unless SPLIT)
 };
 
 struct ObsState {  // per system, observer warp
@@ -192,19 +193,21 @@ struct ObsState {  // per system, observer warp
 #ifndef NB_GRID_VALIDATE_ATTR
 #define NB_GRID_VALIDATE_ATTR __forceinline__
 #endif
+template <int NTHR>
 __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* grec, int R, int st, int tid, int hsel, volatile int* abort_flag,
                                             int* status, unsigned long long* n_stale, int own_lo, int own_hi, volatile int* stale_own) {
     bool patched = false;
-    double2 va[4], vb[4];  // whole records, conflict-free LDS.128 pairs (lanes with bit 2 set read the second half first)
+    constexpr int NK = 1024 / NTHR;  // records per thread (n <= 1024)
+    double2 va[NK], vb[NK];  // whole records, conflict-free LDS.128 pairs (lanes with bit 2 set read the second half first)
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int r = min(tid + 256 * k, R - 1);
+    for (int k = 0; k < NK; k++) {
+        const int r = min(tid + NTHR * k, R - 1);
         va[k] = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
         vb[k] = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int r = tid + 256 * k;
+    for (int k = 0; k < NK; k++) {
+        const int r = tid + NTHR * k;
         const double2 lo = hsel ? vb[k] : va[k], hi = hsel ? va[k] : vb[k];
         if (r < R && !tag_ok(hi.y, st, lo.x, lo.y, hi.x)) {
             double x, y, z, tg;
@@ -231,8 +234,11 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
 }
 
 // PROFILE: block 0 thread 0 accumulates clock64 per phase (NB_GRID_PROFILE=1)
-template <int MATH, int T, int NJ, bool PROFILE>
-__global__ void __launch_bounds__(32 * (2 * NJ + 2), 1)
+// SPLIT (T > 1, NB_GRID_SPLIT=1, off by default: measured slower, see launch_m): every system has its OWN warp set (NJ compute
+// warps that take two j-parts each, an observer warp, a producer thread) and runs at its own pace - two independent "virtual
+// blocks" per SM that share nothing but the FP64 pipe.  Without SPLIT one warp set steps the T systems in turn (lock step).
+template <int MATH, int T, int NJ, bool PROFILE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 32 * T * (NJ + 2) : 32 * (2 * NJ + 2), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
                  long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single, int adapt_up,
                  int adapt_down) {
@@ -241,7 +247,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int n = descs[0].n;
-    constexpr int NCW = 2 * NJ, W_OBS = NCW, W_PROD = NCW + 1, GT = 32 * (NCW + 2), RQ = 32 * NJ;
+    constexpr int PPW = SPLIT ? 2 : 1;  // j-parts per compute warp
+    constexpr int NCW = 2 * NJ / PPW, NSET = SPLIT ? T : 1, W_OBS = NSET * NCW, W_PROD = W_OBS + NSET, GT = 32 * (W_PROD + NSET), RQ = 32 * NJ;
+    constexpr int TL = SPLIT ? 1 : T;  // systems per warp set: a role warp handles systems tb .. tb + TL - 1
     const int RS = (R + RPAD - 1) / RPAD * RPAD;  // records per stage in shared memory (tail beyond R: zero mass, never copied)
     // per system: pos[2][RS] records {x, y, z, tag} then gm[2][RS]
     auto s_pos = [&](int t, int stage) { return smem + (size_t)t * 10 * RS + (size_t)stage * 4 * RS; };
@@ -345,33 +353,36 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         return true;
     };
 
-    if (warp == W_PROD) {
+    if (warp >= W_PROD) {
         // ------------------------------------------------------------------ PRODUCER thread
+        const int tb = SPLIT ? warp - W_PROD : 0;
         if (lane == 0) {
             const uint32_t CS = cluster_nctarank(), rank = cluster_ctarank();
             const uint32_t slice = (uint32_t)R / CS;  // records per cluster rank (R is a multiple of 8*CS)
             const uint16_t mask = (uint16_t)((1u << CS) - 1u);
-            int pstep[T];
-            bool pact[T];
+            int pstep[TL];
+            bool pact[TL];
             bool any = false;
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                pstep[t] = descs[t].step_begin;
-                pact[t] = !sh.stop[t] && descs[t].step_end > descs[t].step_begin;
-                any |= pact[t];
+            for (int u = 0; u < TL; u++) {
+                const int t = tb + u;
+                pstep[u] = descs[t].step_begin;
+                pact[u] = !sh.stop[t] && descs[t].step_end > descs[t].step_begin;
+                any |= pact[u];
             }
             while (any && !sh.abort) {
                 any = false;
 #pragma unroll
-                for (int t = 0; t < T; t++) {
-                    if (!pact[t]) continue;
-                    const int st = pstep[t] + 1;
+                for (int u = 0; u < TL; u++) {
+                    const int t = tb + u;
+                    if (!pact[u]) continue;
+                    const int st = pstep[u] + 1;
                     // wait (hardware-suspended on the mbarrier, no issue slots taken from the compute warps) until this
                     // block's sums of step st are complete: it publishes within ~150 clk, and so does everybody
                     bool go = wait_bar(&sh.trig[t][st & 1], (uint32_t)((st - descs[t].step_begin - 1) >> 1) & 1u);
                     if (sh.stop[t]) go = false;
                     if (!go) {
-                        pact[t] = false;
+                        pact[u] = false;
                         continue;
                     }
                     const long long t1 = clock64();
@@ -381,10 +392,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     // copy reads them.  The blocks keep in step only through the data; whoever copies too early finds stale
                     // tags and polls (validation below), so the delay is a speed knob, not a correctness condition.
                     int dl = adapt_up > 0 ? sh.delay[t] : delay_clk;
-                    if (T > 1 && adapt_up <= 0) {  // the only system still running in this launch waits for every copy: shortest delay
+                    if (TL > 1 && adapt_up <= 0) {  // the only system still running in this launch waits for every copy: shortest delay
                         int n_act = 0;
 #pragma unroll
-                        for (int u = 0; u < T; u++) n_act += pact[u] ? 1 : 0;
+                        for (int w = 0; w < TL; w++) n_act += pact[w] ? 1 : 0;
                         if (n_act == 1) dl = delay_single;
                     }
                     while (clock64() - t1 < dl) {
@@ -395,20 +406,22 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         tma_load(dst, src, slice * 32u, bar);
                     else
                         tma_load_multicast(dst, src, slice * 32u, bar, mask);
-                    pstep[t] = st;
-                    if (st >= descs[t].step_end) pact[t] = false;
-                    any |= pact[t];
+                    pstep[u] = st;
+                    if (st >= descs[t].step_end) pact[u] = false;
+                    any |= pact[u];
                 }
             }
         }
-    } else if (warp == W_OBS) {
+    } else if (warp >= W_OBS) {
         // ------------------------------------------------------------------ OBSERVER warp
-        ObsState os[T];
+        const int tb = SPLIT ? warp - W_OBS : 0;
+        ObsState os[TL];
         bool any = false;
 #pragma unroll
-        for (int t = 0; t < T; t++) {
+        for (int u = 0; u < TL; u++) {
+            const int t = tb + u;
             const TrajDesc& d = descs[t];
-            ObsState& s = os[t];
+            ObsState& s = os[u];
             s.n_dev = d.n_dev, s.kind = d.kind, s.DD = d.destroy_device;
             s.Prec = d.planet, s.Arec = d.asteroid;
             s.DDrec = (s.DD >= 0 && s.DD < n) ? s.DD : 0;
@@ -429,8 +442,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         while (any && !sh.abort) {
             any = false;
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                ObsState& s = os[t];
+            for (int u = 0; u < TL; u++) {
+                const int t = tb + u;
+                ObsState& s = os[u];
                 if (!s.active) continue;
                 const int st = s.step, stage = st & 1;
                 if (st > s.step_begin && !wait_bar(&sh.full[t][stage], (uint32_t)((st - s.step_begin - 1) >> 1) & 1u)) {
@@ -495,9 +509,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         // events (block 0 reports; every block computed the same)
         if (c == 0) {
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                const TrajDesc& d = descs[t];
-                ObsState& s = os[t];
+            for (int u = 0; u < TL; u++) {
+                const TrajDesc& d = descs[tb + u];
+                ObsState& s = os[u];
                 if (lane < s.n_dev) d.ev->reach_step[lane] = s.my_reach;
                 if (lane == 0) {
                     d.ev->min_d2 = s.min_d2;
@@ -513,16 +527,20 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         }
     } else {
         // ------------------------------------------------------------------ COMPUTE warps
-        const int bg = warp / NJ, part = warp % NJ;
+        const int tb = SPLIT ? warp / NCW : 0;          // the warp set's (first) system
+        const int cw = warp - tb * NCW, ctid = tid - tb * 32 * NCW;  // warp / thread index inside the set
+        const int bar_id = 1 + tb;
+        const int bg = cw / (NJ / PPW), part0 = (cw % (NJ / PPW)) * PPW;  // body group, first j-part
         const int body0 = c * GB + bg * BPW;  // the warp's four bodies (records body0 .. body0+3)
         const int hsel = (lane >> 2) & 1;     // conflict-free LDS.128 pairs: these lanes read the second half first
-        // integrator threads (warp 0, lane < 24): body 8c + lane/3, component lane%3
+        // integrator threads (warp 0 of the set, lane < 24): body 8c + lane/3, component lane%3
         const int ib = lane / 3, ik = lane - 3 * ib;
         const int my_body = c * GB + ib;
-        const bool integ = warp == 0 && lane < 3 * GB;
-        int cstep[T], cbegin[T], cend[T];
-        bool cact[T];
-        double iq[T], iv[T];
+        const bool integ = cw == 0 && lane < 3 * GB;
+        double (*spart)[2 * MAX_NJ][3 * BPW] = sh.part[tb];
+        int cstep[TL], cbegin[TL], cend[TL];
+        bool cact[TL];
+        double iq[TL], iv[TL];
         long long pacc[6] = {0, 0, 0, 0, 0, 0}, pt = 0;
         unsigned long long n_stale = 0;
         auto tick = [&](int phase) {
@@ -534,14 +552,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         };
         bool any = false;
 #pragma unroll
-        for (int t = 0; t < T; t++) {
-            const TrajDesc& d = descs[t];
-            cstep[t] = cbegin[t] = d.step_begin, cend[t] = d.step_end;
-            cact[t] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
+        for (int u = 0; u < TL; u++) {
+            const TrajDesc& d = descs[tb + u];
+            cstep[u] = cbegin[u] = d.step_begin, cend[u] = d.step_end;
+            cact[u] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
             const bool mine = integ && my_body < n;
-            iq[t] = mine ? d.q[ik * n + my_body] : 0.0;
-            iv[t] = mine ? d.v[ik * n + my_body] : 0.0;
-            any |= cact[t];
+            iq[u] = mine ? d.q[ik * n + my_body] : 0.0;
+            iv[u] = mine ? d.v[ik * n + my_body] : 0.0;
+            any |= cact[u];
         }
         long long g0 = 0, c0 = 0;
         if (PROFILE) {
@@ -553,13 +571,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
 
         while (any && !aborted) {
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                if (!cact[t]) continue;  // uniform across the grid
+            for (int u = 0; u < TL; u++) {
+                const int t = tb + u;
+                if (!cact[u]) continue;  // uniform across the grid
                 if (PROFILE) pt = clock64();
-                const int st = cstep[t], stage = st & 1;
-                const bool last = st >= cend[t];
+                const int st = cstep[u], stage = st & 1;
+                const bool last = st >= cend[u];
                 // a failed wait has raised sh.abort: the warps still meet at this step's barriers and leave together below
-                if (!last && st > cbegin[t]) wait_bar(&sh.full[t][stage], (uint32_t)((st - cbegin[t] - 1) >> 1) & 1u);
+                if (!last && st > cbegin[u]) wait_bar(&sh.full[t][stage], (uint32_t)((st - cbegin[u] - 1) >> 1) & 1u);
                 tick(0);
                 double* pos = s_pos(t, stage);
                 const double* cg = s_gm(t, stage);
@@ -573,12 +592,12 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
                     //     memory and patch shared memory, each stale record by exactly one thread of the block.
                     const int own_lo = (int)cluster_ctarank() * (R / (int)cluster_nctarank());
-                    const bool patched = validate_stage(pos, grec, R, st, tid, hsel, &sh.abort, status, &n_stale, own_lo,
+                    const bool patched = validate_stage<32 * NCW>(pos, grec, R, st, ctid, hsel, &sh.abort, status, &n_stale, own_lo,
                                                         own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
                     // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
                     if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    compute_bar<32 * NCW>();
-                    if (adapt_up > 0 && tid == 0) {
+                    compute_bar<32 * NCW>(bar_id);
+                    if (adapt_up > 0 && ctid == 0) {
                         // closed loop on the copy delay: stale records in the slice this block's producer copied = it copied
                         // too early (raise the delay by adapt_up); a clean step lowers it by adapt_down.  The slowest
                         // block never sees stale records, so ITS delay - the one on the critical path - decays to the floor.
@@ -593,11 +612,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     }
                 }
                 tick(5);
-                for (int attempt = 0; attempt < 2; attempt++) {
+                // (1) forces on the warp's four bodies (nbody.cc:56-74) from j-part `jp` of the records
+                auto pairs_part = [&](int jp) {
 #pragma unroll
                     for (int i = 0; i < BPW; i++) ax[i] = ay[i] = az[i] = 0.0;
                     if (!last) {
-                        // (1) forces on the warp's four bodies (nbody.cc:56-74) from its part of the records
                         double xi[BPW], yi[BPW], zi[BPW];
 #pragma unroll
                         for (int i = 0; i < BPW; i++) {
@@ -605,7 +624,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                             xi[i] = p[0], yi[i] = p[1], zi[i] = p[2];
                         }
 #pragma unroll 2
-                        for (int r = 32 * part + lane; r < RS; r += RQ) {
+                        for (int r = 32 * jp + lane; r < RS; r += RQ) {
                             // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
                             const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
                             const double2 B = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * (hsel ^ 1));
@@ -615,23 +634,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                             for (int i = 0; i < BPW; i++) pair<MATH>(xi[i], yi[i], zi[i], jx, jy, jz, jg, ax[i], ay[i], az[i]);
                         }
                     }
-                    tick(1);
-                    // (2) the observer's verdict on the positions of step st
-                    flags = wait_bar(&sh.obs[t][stage], (uint32_t)((st - cbegin[t]) >> 1) & 1u) ? sh.flags[t][stage] : 0;
-                    if (!(flags & FLAG_REDO)) break;  // else: the device was destroyed at this very step, once per trajectory
-                }
-                tick(2);
-                if (flags & FLAG_STOP) {
-                    cact[t] = false;
-                    if (tid == 0) {  // releases the producer, which waits for the trigger of step st + 1
-                        sh.stop[t] = 1;
-                        __threadfence_block();
-                        mbar_arrive(&sh.trig[t][(st + 1) & 1]);
-                    }
-                    continue;
-                }
-                // (3) transposing butterfly: 12 sums -> lanes 0/8/16/24 hold body 0/1/2/3
-                {
+                };
+                // (3) transposing butterfly: 12 sums -> lanes 0/8/16/24 hold body 0/1/2/3; into the slot of (body group, j-part)
+                auto butterfly_store = [&](int jp) {
                     const bool h16 = lane & 16, h8 = lane & 8;
                     double k[6];
 #pragma unroll
@@ -656,42 +661,72 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         m2 += __shfl_xor_sync(0xffffffffu, m2, o);
                     }
                     if ((lane & 7) == 0) {
-                        double* dstp = &sh.part[pbuf][warp][3 * (lane >> 3)];
+                        double* dstp = &spart[pbuf][bg * NJ + jp][3 * (lane >> 3)];
                         dstp[0] = m0, dstp[1] = m1, dstp[2] = m2;
                     }
+                };
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    if (PPW == 1) {
+                        pairs_part(part0);
+                        tick(1);
+                    } else {
+                        // a warp of a SPLIT set takes PPW j-parts one after the other, each summed and reduced exactly as a
+                        // warp of the 8-warp set does it: the arithmetic (and so every bit of the state) is the same
+#pragma unroll 1
+                        for (int pp = 0; pp < PPW; pp++) {
+                            pairs_part(part0 + pp);
+                            tick(1);
+                            butterfly_store(part0 + pp);
+                            tick(3);
+                        }
+                    }
+                    // (2) the observer's verdict on the positions of step st
+                    flags = wait_bar(&sh.obs[t][stage], (uint32_t)((st - cbegin[u]) >> 1) & 1u) ? sh.flags[t][stage] : 0;
+                    if (!(flags & FLAG_REDO)) break;  // else: the device was destroyed at this very step, once per trajectory
                 }
+                tick(2);
+                if (flags & FLAG_STOP) {
+                    cact[u] = false;
+                    if (ctid == 0) {  // releases the producer, which waits for the trigger of step st + 1
+                        sh.stop[t] = 1;
+                        __threadfence_block();
+                        mbar_arrive(&sh.trig[t][(st + 1) & 1]);
+                    }
+                    continue;
+                }
+                if (PPW == 1) butterfly_store(part0);
                 tick(3);
-                compute_bar<32 * NCW>();
+                compute_bar<32 * NCW>(bar_id);
                 if (sh.abort) {  // an exchange wait timed out somewhere in this block
                     aborted = true;
                     break;
                 }
                 // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
                 //     tagged sector {x, y, z, step}, unfenced
-                if (warp == 0) {
+                if (cw == 0) {
                     if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
                     if (integ) {
-                        const double* p = &sh.part[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
+                        const double* p = &spart[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
                         double a = p[0];
 #pragma unroll
                         for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
-                        if (my_body < n) kick_drift(a, iv[t], iq[t]);
+                        if (my_body < n) kick_drift(a, iv[u], iq[u]);
                     }
-                    const double qy = __shfl_down_sync(0xffffffffu, iq[t], 1);
-                    const double qz = __shfl_down_sync(0xffffffffu, iq[t], 2);
-                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[t], qy, qz, make_tag(st + 1, iq[t], qy, qz));
+                    const double qy = __shfl_down_sync(0xffffffffu, iq[u], 1);
+                    const double qz = __shfl_down_sync(0xffffffffu, iq[u], 2);
+                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[u], qy, qz, make_tag(st + 1, iq[u], qy, qz));
                 }
-                cstep[t] = st + 1;
+                cstep[u] = st + 1;
                 pbuf ^= 1;
                 tick(4);
             }
             any = false;
 #pragma unroll
-            for (int t = 0; t < T; t++) any |= cact[t];
+            for (int u = 0; u < TL; u++) any |= cact[u];
         }
-        if (aborted && tid == 0) {
+        if (aborted && ctid == 0) {
 #pragma unroll
-            for (int t = 0; t < T; t++) sh.stop[t] = 1;
+            for (int u = 0; u < TL; u++) sh.stop[tb + u] = 1;
         }
 
         if (PROFILE) {
@@ -707,10 +742,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         // write back
         if (integ && my_body < n) {
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                const TrajDesc& d = descs[t];
-                d.q[ik * n + my_body] = iq[t];
-                d.v[ik * n + my_body] = iv[t];
+            for (int u = 0; u < TL; u++) {
+                const TrajDesc& d = descs[tb + u];
+                d.q[ik * n + my_body] = iq[u];
+                d.v[ik * n + my_body] = iv[u];
             }
         }
     }
@@ -748,9 +783,9 @@ WsLayout ws_layout(int n, int T) {
     return w;
 }
 
-template <int MATH, int T, int NJ>
+template <int MATH, int T, int NJ, bool SPLIT = false>
 int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
-    constexpr int GT = 32 * (2 * NJ + 2);
+    constexpr int GT = SPLIT ? 32 * T * (NJ + 2) : 32 * (2 * NJ + 2);
     const int C = padded_blocks(n, cs);
     const size_t smem = smem_for(n, T, cs);
     const WsLayout w = ws_layout(n, MAX_T);  // one layout for every T: the status word has a fixed place
@@ -763,11 +798,13 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     // 1100; on another box 750 gave 3.9 and 900 gave 3.2, so 900 it is); with two systems in lock step the copy of one hides
     // behind the pair loop of the other and a longer delay (fewer stale records, fewer polls) wins (measured: b1024
     // four-trajectory solve on one GPU 2.33 s at 900, 2.00 s at 2600)
-    static const int delay_clk_env = env_int("NB_GRID_DELAY", T == 1 ? 900 : 2600);
+    // SPLIT: every system has its own warp set and timeline, i.e. behaves like a single system
+    static const int delay_clk_env = (T == 1 || SPLIT) ? env_int("NB_GRID_DELAY", 900) : env_int("NB_GRID_DELAY2", 3400);
     static const int delay_single_env = env_int("NB_GRID_DELAY", 900);
-    auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true> : grid_traj_kernel<MATH, T, NJ, false>;
+    auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true, SPLIT> : grid_traj_kernel<MATH, T, NJ, false, SPLIT>;
     NB_CUDA(cudaMemsetAsync(ws, 0, w.gbuf_bytes, stream));  // tag 0 = no step
     if (profile) NB_CUDA(cudaMemsetAsync(prof, 0, NPROF * sizeof(long long), stream));
+
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) {
         const unsigned long long big = ~0ULL;
@@ -828,7 +865,13 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
         return true;
     }();
     (void)adapt_read;
-    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single, adapt_up, adapt_down));
+    // two systems in lock step (T > 1, not SPLIT): the copy of one system hides behind the other's step, so the delay is a
+    // constant in the middle of that window (NB_GRID_DELAY2) - measured on B200, b1024 three-query solve on one GPU: adaptive
+    // (capped at 1600 clk) 1.45 s with 36 000 stale records per step, constant 2600: 1.33 - 1.40 s, 3400: 1.32 s with 170,
+    // 5000: 1.39 s, 7000: 1.78 s; NB_GRID_ADAPT2=1 turns the closed loop on there too
+    static const int adapt2 = env_int("NB_GRID_ADAPT2", 0);
+    const int a_up = (T == 1 || SPLIT || adapt2) ? adapt_up : 0;
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, descs, fst, gbuf, prof, status, R, delay_clk, delay_single, a_up, adapt_down));
     count_launch();
     {
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
@@ -857,6 +900,14 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
 template <int MATH>
 int launch_m(int T, int n, int cs, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
     if (T == 1) return launch_t<MATH, 1, 4>(n, cs, descs, fst, ws, stream);
+    // Two systems per launch: one set of 8 compute warps steps both in turn (lock step: the exchange of one system hides
+    // behind the other's step).  NB_GRID_SPLIT=1: each system has its own set of 4 compute warps, observer and producer and
+    // runs at its own pace - same arithmetic, same results; measured SLOWER (b1024 three-query solve on one GPU 1.35 - 1.46 s
+    // against 1.27 s): one compute warp per scheduler keeps the FP64 pipe only 33 % busy (ncu: 49 % of its pair-loop samples
+    // wait on fixed-latency dependencies, 17 % on MUFU.RSQ64H), two warps of the same system 76 %, so two half-speed systems
+    // side by side do not beat two full-speed systems in turn (profiles/r02_grid_exchange.md, section 5).
+    static const int split = env_int("NB_GRID_SPLIT", 0);
+    if (split) return launch_t<MATH, 2, 4, true>(n, cs, descs, fst, ws, stream);
     return launch_t<MATH, 2, 4>(n, cs, descs, fst, ws, stream);
 }
 
@@ -912,8 +963,8 @@ bool grid_traj_supported(int gpu, int n, int n_traj) {
 
 void grid_traj_warm() {
     cudaFuncAttributes fa;
-    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 1, 4, false>);
-    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 2, 4, false>);
+    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 1, 4, false, false>);
+    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 2, 4, false, true>);
 }
 
 // device address of the status word of a workspace: 0 = ok, 1 = an exchange spin timed out (read after the stream is idle)

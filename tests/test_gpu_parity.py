@@ -321,7 +321,7 @@ def test_grid_exchange_knobs_never_change_results_full_length(nb):
     """The fence-free exchange of the grid kernel (self-checking 32-byte records, TMA multicast, poll-and-patch) is
     timing-dependent by design; its RESULTS must not be.  b1024 and b512, all 200 000 steps, with clusters of 1 / 2 / 4,
     the copy issued with no delay at all (every record stale at first: all go through the poll-and-patch path), one
-    or two systems per launch: final q and v bit-identical, same events."""
+    or two systems per launch (in lock step, or each with its own warp set): final q and v bit-identical, same events."""
     import sys
     code = ("import importlib, hashlib, json, sys\n"
             "sys.path.insert(0, %r)\n"
@@ -340,7 +340,8 @@ def test_grid_exchange_knobs_never_change_results_full_length(nb):
     for name, knobs in (("default", {}), ("cs1", dict(NB_GRID_CS="1")), ("cs2_t1", dict(NB_GRID_CS="2", NB_GRID_T="1")),
                         ("cs4_delay0", dict(NB_GRID_CS="4", NB_GRID_DELAY="0")), ("cs2_delay0_t2", dict(NB_GRID_CS="2", NB_GRID_DELAY="0", NB_GRID_T="2")),
                         ("delay5000_constant", dict(NB_GRID_DELAY="5000", NB_GRID_ADAPT="0,0")), ("constant900", dict(NB_GRID_ADAPT="0,0")),
-                        ("adapt_fast", dict(NB_GRID_ADAPT="400,100"))):
+                        ("adapt_fast", dict(NB_GRID_ADAPT="400,100")), ("split_sets", dict(NB_GRID_SPLIT="1")),
+                        ("lockstep_adaptive_delay0", dict(NB_GRID_ADAPT2="1", NB_GRID_DELAY2="0"))):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, **knobs), timeout=900)
         assert r.returncode == 0, (name, r.stderr.decode()[-2000:])
         results[name] = json.loads(r.stdout.decode().strip().split("\n")[-1])

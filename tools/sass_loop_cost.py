@@ -1,0 +1,106 @@
+"""FP64 issue-cost model of the hottest loop of a kernel (the innermost backward branch that spans the most FP64
+instructions), read from `cuobjdump -sass`.
+
+    python tools/sass_loop_cost.py <cubin|.o|.so> <kernel name substring> [min_fp64]
+
+Model (measured on B200, profiles/r02_fp64_ops_raw.log): an FP64 instruction costs 2 pipe cycles per warp and SM
+sub-partition with up to two distinct register-pair operands, 3 with three; an operand that the PREVIOUS instruction left
+in the operand-reuse cache (same slot, `.reuse` flag) is free (2.2 measured, counted as 2).  SHFL / MUFU / LDS beside the
+FP64 stream cost extra (fp64_mix): SHFL + 0.7, MUFU.RSQ64H + 0.5 / 8.
+"""
+import collections
+import re
+import subprocess
+import sys
+
+
+def functions(path):
+    out = subprocess.check_output(["cuobjdump", "-sass", path]).decode()
+    for b in re.split(r"\n\s*Function : ", out)[1:]:
+        name, body = b.split("\n", 1)
+        yield name.strip(), body
+
+
+def parse(body):
+    ins = []
+    for line in body.split("\n"):
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if not m:
+            continue
+        addr = int(m.group(1), 16)
+        text = m.group(2).strip()
+        pm = re.match(r"(@!?U?P\d+\s+)?(\S+)\s*(.*)", text)
+        op = pm.group(2)
+        args = [a.strip() for a in pm.group(3).split(",")] if pm.group(3) else []
+        ins.append((addr, op, args, text))
+    return ins
+
+
+def fp64_cost(ins):
+    """returns (n_fp64, cycles, histogram) for a list of instructions in program order"""
+    prev = None
+    n = cyc = 0
+    hist = collections.Counter()
+    for addr, op, args, text in ins:
+        base = op.split(".")[0]
+        if base not in ("DFMA", "DMUL", "DADD"):
+            prev = None
+            continue
+        srcs = args[1:]
+        regs = [re.sub(r"[-|]|\.reuse", "", a) for a in srcs if re.match(r"-?\|?R\d", a)]
+        distinct = len(set(regs))
+        free = 0
+        if prev is not None:
+            seen = set()
+            for k, a in enumerate(srcs):
+                r = re.sub(r"[-|]|\.reuse", "", a)
+                if k < len(prev) and ".reuse" in prev[k] and re.sub(r"[-|]|\.reuse", "", prev[k]) == r and r not in seen:
+                    free += 1
+                    seen.add(r)
+        c = max(2, distinct - free)
+        hist[(base, distinct, free)] += 1
+        n += 1
+        cyc += c
+        prev = srcs
+    return n, cyc, hist
+
+
+def main():
+    path, fun = sys.argv[1], sys.argv[2]
+    min_fp64 = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    for name, body in functions(path):
+        if fun not in name:
+            continue
+        ins = parse(body)
+        addr_index = {a: i for i, (a, _, _, _) in enumerate(ins)}
+        loops = []
+        for i, (addr, op, args, text) in enumerate(ins):
+            if op.startswith("BRA") and args:
+                m = re.match(r"(0x[0-9a-f]+)", args[-1])
+                if m:
+                    tgt = int(m.group(1), 16)
+                    if tgt <= addr and tgt in addr_index:
+                        loops.append((addr_index[tgt], i))
+        print(name[:110])
+        # innermost loops only: no other loop strictly inside
+        for (a, b) in loops:
+            if any((c > a or d < b) and c >= a and d <= b for (c, d) in loops if (c, d) != (a, b)):
+                continue
+            seg = ins[a:b + 1]
+            n, cyc, hist = fp64_cost(seg)
+            if n < min_fp64:
+                continue
+            ops = collections.Counter(o.split(".")[0] for _, o, _, _ in seg)
+            extra = 0.7 * ops["SHFL"] + 0.5 * ops["MUFU"] / 1.0 * 0.125 * 8 * 0.125
+            acc3 = sum(v for (o, d, f), v in hist.items() if o == "DFMA" and d == 3)
+            acc3_free = sum(v for (o, d, f), v in hist.items() if o == "DFMA" and d == 3 and f >= 1)
+            print("  loop 0x%x..0x%x: %d instr, %d FP64 (%d three-operand DFMA, %d of them with a reuse hit), FP64 pipe cycles %d "
+                  "(%.3f per FP64 instr; ideal %d), SHFL %d MUFU %d LDS %d other %d"
+                  % (ins[a][0], ins[b][0], len(seg), n, acc3, acc3_free, cyc, cyc / max(n, 1), 2 * n, ops["SHFL"], ops["MUFU"],
+                     ops["LDS"], len(seg) - n - ops["SHFL"] - ops["MUFU"] - ops["LDS"]))
+            print("    issue-rate ceiling from operand fetch: %.1f %%; with shuffles (+0.7 each): %.1f %%"
+                  % (200.0 * n / cyc, 200.0 * n / (cyc + 0.7 * ops["SHFL"])))
+
+
+if __name__ == "__main__":
+    main()

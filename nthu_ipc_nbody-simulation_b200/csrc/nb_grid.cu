@@ -65,6 +65,10 @@
 #include "nb_internal.h"
 #include "nb_math.cuh"
 
+#ifndef NB_GRID_V0_SKIP
+#define NB_GRID_V0_SKIP 1
+#endif
+
 namespace nb {
 
 namespace {
@@ -148,10 +152,22 @@ __device__ __forceinline__ void compute_bar(int id) { asm volatile("bar.sync %0,
 // before its publication is old in all four words: the common case, handled in the validation pass); both are made in
 // the validation pass (validate_stage, kept out of line so that the pair loop's code generation does not depend on it).
 __device__ __forceinline__ unsigned fold32(double x, double y, double z) {
+    // rot13(the four words of the record's first half) ^ the two words of z: two 3-input LOP3, one funnel shift, one LOP3 -
+    // the check is on the serial path of every step (publication) and is made for every record of every step (validation)
     const unsigned lx = (unsigned)__double2loint(x), hx = (unsigned)__double2hiint(x), ly = (unsigned)__double2loint(y),
                    hy = (unsigned)__double2hiint(y), lz = (unsigned)__double2loint(z), hz = (unsigned)__double2hiint(z);
-    return lx ^ __funnelshift_l(hx, hx, 5) ^ __funnelshift_l(ly, ly, 11) ^ __funnelshift_l(hy, hy, 17) ^
-           __funnelshift_l(lz, lz, 23) ^ __funnelshift_l(hz, hz, 29);
+    const unsigned h = lx ^ hx ^ ly ^ hy;
+    return __funnelshift_l(h, h, 13) ^ lz ^ hz;
+}
+// the same check on a record as the validation pass holds it: two 16-byte halves A (read first) and B, which of them is the
+// record's first half depends on the lane (hsel: conflict-free LDS.128 pairs).  Four selects instead of swapping eight words.
+__device__ __forceinline__ bool halves_ok(double2 A, double2 B, int hsel, int step) {
+    const unsigned pa = (unsigned)__double2loint(A.x) ^ (unsigned)__double2hiint(A.x) ^ (unsigned)__double2loint(A.y);
+    const unsigned pb = (unsigned)__double2loint(B.x) ^ (unsigned)__double2hiint(B.x) ^ (unsigned)__double2loint(B.y);
+    const unsigned sa = (unsigned)__double2hiint(A.y), sb = (unsigned)__double2hiint(B.y);
+    // first half {x, y}: all four words; second half {z, tag}: z's two words and the tag's low word, the tag's high word is the step
+    const unsigned first = (hsel ? pb ^ sb : pa ^ sa), second = hsel ? pa : pb, stp = hsel ? sa : sb;
+    return (int)stp == step && (__funnelshift_l(first, first, 13) ^ second) == 0u;
 }
 __device__ __forceinline__ double make_tag(int step, double x, double y, double z) {
     return __hiloint2double(step, (int)fold32(x, y, z));
@@ -197,7 +213,7 @@ template <int NTHR>
 __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* grec, int R, int st, int tid, int hsel, volatile int* abort_flag,
                                             int* status, unsigned long long* n_stale, int own_lo, int own_hi, volatile int* stale_own) {
     bool patched = false;
-    constexpr int NK = 1024 / NTHR;  // records per thread (n <= 1024)
+    constexpr int NK = (1024 + NTHR - 1) / NTHR;  // records per thread (n <= 1024)
     double2 va[NK], vb[NK];  // whole records, conflict-free LDS.128 pairs (lanes with bit 2 set read the second half first)
 #pragma unroll
     for (int k = 0; k < NK; k++) {
@@ -208,8 +224,7 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
 #pragma unroll
     for (int k = 0; k < NK; k++) {
         const int r = tid + NTHR * k;
-        const double2 lo = hsel ? vb[k] : va[k], hi = hsel ? va[k] : vb[k];
-        if (r < R && !tag_ok(hi.y, st, lo.x, lo.y, hi.x)) {
+        if (r < R && !halves_ok(va[k], vb[k], hsel, st)) {
             double x, y, z, tg;
             const long long t0 = clock64();
             do {
@@ -221,7 +236,8 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
                     break;
                 }
             } while (!tag_ok(tg, st, x, y, z));
-            if (tag_step_is(hi.y, st)) atomicAdd(status + 1, 1);  // right step, wrong fold: a TORN record (word 1 of the status block)
+            // right step, wrong fold: a TORN record (word 1 of the status block)
+            if (tag_step_is(hsel ? va[k].y : vb[k].y, st)) atomicAdd(status + 1, 1);
             pos[4 * r] = x, pos[4 * r + 1] = y, pos[4 * r + 2] = z;
             __threadfence_block();
             pos[4 * r + 3] = tg;
@@ -592,8 +608,16 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
                     //     memory and patch shared memory, each stale record by exactly one thread of the block.
                     const int own_lo = (int)cluster_ctarank() * (R / (int)cluster_nctarank());
-                    const bool patched = validate_stage<32 * NCW>(pos, grec, R, st, ctid, hsel, &sh.abort, status, &n_stale, own_lo,
-                                                        own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
+                    // Several systems in lock step: warp 0 comes late from the previous system's integration and publication,
+                    // so the other warps validate without it (NB_GRID_V0: A/B knob) and it only joins the barrier.
+                    constexpr bool SKIP0 = (TL > 1) && NB_GRID_V0_SKIP;
+                    bool patched = false;
+                    if (!SKIP0)
+                        patched = validate_stage<32 * NCW>(pos, grec, R, st, ctid, hsel, &sh.abort, status, &n_stale, own_lo,
+                                                           own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
+                    else if (cw != 0)
+                        patched = validate_stage<32 * (NCW - 1)>(pos, grec, R, st, ctid - 32, hsel, &sh.abort, status, &n_stale, own_lo,
+                                                                 own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
                     // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
                     if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     compute_bar<32 * NCW>(bar_id);

@@ -65,10 +65,6 @@
 #include "nb_internal.h"
 #include "nb_math.cuh"
 
-#ifndef NB_GRID_V0_SKIP
-#define NB_GRID_V0_SKIP 1
-#endif
-
 namespace nb {
 
 namespace {
@@ -608,16 +604,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     //     before its publication - this is how the fast blocks wait for the slowest: poll that sector in global
                     //     memory and patch shared memory, each stale record by exactly one thread of the block.
                     const int own_lo = (int)cluster_ctarank() * (R / (int)cluster_nctarank());
-                    // Several systems in lock step: warp 0 comes late from the previous system's integration and publication,
-                    // so the other warps validate without it (NB_GRID_V0: A/B knob) and it only joins the barrier.
-                    constexpr bool SKIP0 = (TL > 1) && NB_GRID_V0_SKIP;
-                    bool patched = false;
-                    if (!SKIP0)
-                        patched = validate_stage<32 * NCW>(pos, grec, R, st, ctid, hsel, &sh.abort, status, &n_stale, own_lo,
-                                                           own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
-                    else if (cw != 0)
-                        patched = validate_stage<32 * (NCW - 1)>(pos, grec, R, st, ctid - 32, hsel, &sh.abort, status, &n_stale, own_lo,
-                                                                 own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
+                    // (measured worse with two systems in lock step: warps 1-7 validating while warp 0 still integrates and
+                    // publishes the other system - 1.31 s against 1.27 s for the b1024 solve on one GPU)
+                    const bool patched = validate_stage<32 * NCW>(pos, grec, R, st, ctid, hsel, &sh.abort, status, &n_stale, own_lo,
+                                                                  own_lo + R / (int)cluster_nctarank(), &sh.stale_own[t]);
                     // generic-proxy writes to a buffer the async proxy (TMA) overwrites two steps later
                     if (patched) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     compute_bar<32 * NCW>(bar_id);

@@ -192,8 +192,8 @@ struct ObsState {  // per system, observer warp
     bool q3_armed, active, observed;
     double min_d2, cost;
     int argmin_step, hit_step, destroyed_step;
-    int my_dev, my_reach;  // lane k < n_dev
-    double my_m0;
+    int my_dev[2], my_reach[2];  // devices lane and lane + 32 of the system's list (-1: none): up to NB_MAX_DEVICES = 64
+    double my_m0[2];
 };
 
 // The validation pass of the compute warps (256 threads, thread tid checks records tid + 256k): every record of the stage
@@ -443,11 +443,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             s.q3_armed = (s.kind == NB_KIND_Q3) && s.DD >= 0 && s.DD < n && d.m[s.DD] != 0.0;
             s.active = !((s.kind >= NB_KIND_Q2) && s.hit_step != -2);
             s.observed = d.ev->steps_done >= s.step;
-            s.my_dev = -1, s.my_reach = -2, s.my_m0 = 0.0;
-            if (lane < s.n_dev) {
-                s.my_dev = d.dev_index[lane];
-                s.my_m0 = d.m[s.my_dev];
-                s.my_reach = d.ev->reach_step[lane];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                s.my_dev[h] = -1, s.my_reach[h] = -2, s.my_m0[h] = 0.0;
+                if (lane + 32 * h < s.n_dev) {
+                    s.my_dev[h] = d.dev_index[lane + 32 * h];
+                    s.my_m0[h] = d.m[s.my_dev[h]];
+                    s.my_reach[h] = d.ev->reach_step[lane + 32 * h];
+                }
             }
             any |= s.active;
         }
@@ -475,12 +478,14 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         s.min_d2 = d2;
                         s.argmin_step = st;
                     }
-                    if (s.kind == NB_KIND_Q2 && s.my_dev >= 0 && s.my_reach == -2) {  // hw5.cu:265-287
-                        double dx, dy, dz;
-                        load_rec(pos, grec, s.my_dev, st, dx, dy, dz);
-                        const double md = __dmul_rn(MISSILE_STEP, (double)st);
-                        if (dist2_rn(px, py, pz, dx, dy, dz) < __dmul_rn(md, md)) s.my_reach = st;
-                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        if (s.kind == NB_KIND_Q2 && s.my_dev[h] >= 0 && s.my_reach[h] == -2) {  // hw5.cu:265-287
+                            double dx, dy, dz;
+                            load_rec(pos, grec, s.my_dev[h], st, dx, dy, dz);
+                            const double md = __dmul_rn(MISSILE_STEP, (double)st);
+                            if (dist2_rn(px, py, pz, dx, dy, dz) < __dmul_rn(md, md)) s.my_reach[h] = st;
+                        }
                     if (s.kind >= NB_KIND_Q2) {
                         if (d2 < PLANET_RADIUS2) {  // nbody.cc:134, hw5.cu:295-298
                             s.hit_step = st;
@@ -500,11 +505,13 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     }
                 }
                 if (st >= s.step_end) flags |= FLAG_STOP;
-                if (!(flags & FLAG_STOP) && s.my_dev >= 0) {
-                    // mass column of the next step's positions: G*m_eff(st + 2) (nbody.cc:14-16, 61-64), 0 once destroyed
-                    const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev == s.DD && s.destroyed_step != -2;
-                    s_gm(t, stage ^ 1)[s.my_dev] = gm_eff(gone ? 0.0 : s.my_m0, true, fst[st + 2]);
-                }
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (!(flags & FLAG_STOP) && s.my_dev[h] >= 0) {
+                        // mass column of the next step's positions: G*m_eff(st + 2) (nbody.cc:14-16, 61-64), 0 once destroyed
+                        const bool gone = (s.kind == NB_KIND_Q3) && s.my_dev[h] == s.DD && s.destroyed_step != -2;
+                        s_gm(t, stage ^ 1)[s.my_dev[h]] = gm_eff(gone ? 0.0 : s.my_m0[h], true, fst[st + 2]);
+                    }
                 __syncwarp();
                 if (lane == 0) {
                     sh.flags[t][stage] = flags;
@@ -524,7 +531,9 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             for (int u = 0; u < TL; u++) {
                 const TrajDesc& d = descs[tb + u];
                 ObsState& s = os[u];
-                if (lane < s.n_dev) d.ev->reach_step[lane] = s.my_reach;
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    if (lane + 32 * h < s.n_dev) d.ev->reach_step[lane + 32 * h] = s.my_reach[h];
                 if (lane == 0) {
                     d.ev->min_d2 = s.min_d2;
                     d.ev->argmin_step = s.argmin_step;

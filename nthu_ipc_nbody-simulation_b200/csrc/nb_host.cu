@@ -215,9 +215,10 @@ struct DeviceBatch {
         const auto h0 = std::chrono::steady_clock::now();
         int max_dev = 0;
         for (int s = 0; s < S; s++) max_dev = h_descs[s].n_dev > max_dev ? h_descs[s].n_dev : max_dev;
-        // the grid kernel keeps one device per lane; STRICT needs the single block's ascending-j sum
+        // the grid kernel's observer warp keeps two devices per lane (NB_MAX_DEVICES = 64); STRICT needs the single block's
+        // ascending-j sum
         bool grid = false;
-        if (allow_grid && math == NB_MATH_FAST && max_dev <= 32 && grid_traj_supported(gpu, n, S)) {
+        if (allow_grid && math == NB_MATH_FAST && max_dev <= 64 && grid_traj_supported(gpu, n, S)) {
             size_t need = grid_traj_workspace_bytes(n, S);
             if (need > grid_ws_bytes) {
                 if (grid_ws) NB_CUDA(cudaFree(grid_ws));

@@ -206,6 +206,34 @@ def test_trajectory_events_match_oracle(nb, oracle):
         t.close()
 
 
+@pytest.mark.parametrize("n_dev", [33, 40, 64])
+def test_grid_kernel_more_than_32_devices(nb, oracle, n_dev):
+    """The grid kernel's observer warp keeps two gravity devices per lane (NB_MAX_DEVICES = 64; hw5.cu:265-309 loops over
+    the devices on one thread).  b200 with n_dev of its bodies declared devices: query 2 (every device's missile-reach step)
+    and a query-3 trajectory of a device of the second half of the list against the oracle, 30 000 steps."""
+    import copy
+    s = copy.copy(nb.read_input(case_path("b200")))
+    dev = np.zeros(s.n, dtype=np.uint8)
+    ids = [i for i in range(s.n) if i not in (s.planet, s.asteroid)][-n_dev:]
+    dev[ids] = 1
+    s.is_device = dev
+    steps = 30000
+    for kind, okind, dd in ((nb.KIND_Q2, oracle.KIND_Q2, -1), (nb.KIND_Q3, oracle.KIND_Q3, 197), (nb.KIND_Q3, oracle.KIND_Q3, ids[32])):
+        t = nb.Trajectory(s, kind, dd)
+        ev = t.run(steps)
+        oev, qo, vo = oracle.trajectory(oracle.MODE_SQRT3, okind, s, dd, n_steps=steps)
+        assert ev.n_reach == oev.n_reach == n_dev
+        assert list(ev.reach_step[:n_dev]) == list(oev.reach_step[:n_dev])
+        assert (ev.hit_step, ev.destroyed_step, ev.argmin_step, ev.steps_done, ev.cost) == \
+               (oev.hit_step, oev.destroyed_step, oev.argmin_step, oev.steps_done, oev.cost)
+        assert abs(ev.min_d2 - oev.min_d2) <= 2e-6 * oev.min_d2
+        q, v, m, step = t.state()
+        assert ulps(q, qo).max() <= 4
+        if kind == nb.KIND_Q3 and ev.destroyed_step != -2:
+            assert m[dd] == 0.0
+        t.close()
+
+
 def test_trajectory_resume_and_fork(nb):
     """Stopping and resuming a persistent trajectory changes nothing; a fork at the missile-reach
     step (hw5.cu:275-284 snapshot -> :482-483 restore) equals the trajectory simulated from step 0."""

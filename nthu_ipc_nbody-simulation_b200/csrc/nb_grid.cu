@@ -184,6 +184,7 @@ struct Shared {
     volatile int abort;
     volatile int delay[MAX_T];      // copy delay after the trigger (clk): a constant, or steered by stale_own (adaptive mode)
     volatile int stale_own[MAX_T];  // this step's validation found stale records in the slice this block's producer copied
+    double iqv[MAX_T][2][32];       // several systems per warp set: position / velocity component of the integrator lanes
     double part[MAX_T][2][2 * MAX_NJ][3 * BPW];  // per compute warp: sums {ax, ay, az} of its 4 bodies over its j-part ([0] unless SPLIT)
 };
 
@@ -580,6 +581,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             const bool mine = integ && my_body < n;
             iq[u] = mine ? d.q[ik * n + my_body] : 0.0;
             iv[u] = mine ? d.v[ik * n + my_body] : 0.0;
+            if (TL > 1 && cw == 0) sh.iqv[tb + u][0][lane] = iq[u], sh.iqv[tb + u][1][lane] = iv[u];
             any |= cact[u];
         }
         long long g0 = 0, c0 = 0;
@@ -733,11 +735,18 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         double a = p[0];
 #pragma unroll
                         for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
-                        if (my_body < n) kick_drift(a, iv[u], iq[u]);
+                        if (TL > 1) {  // state of the other systems stays out of the pair loop's registers
+                            double q_ = sh.iqv[t][0][lane], v_ = sh.iqv[t][1][lane];
+                            if (my_body < n) kick_drift(a, v_, q_);
+                            sh.iqv[t][0][lane] = q_, sh.iqv[t][1][lane] = v_;
+                            iq[0] = q_;
+                        } else if (my_body < n)
+                            kick_drift(a, iv[u], iq[u]);
                     }
-                    const double qy = __shfl_down_sync(0xffffffffu, iq[u], 1);
-                    const double qz = __shfl_down_sync(0xffffffffu, iq[u], 2);
-                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[u], qy, qz, make_tag(st + 1, iq[u], qy, qz));
+                    const double qx = TL > 1 ? iq[0] : iq[u];
+                    const double qy = __shfl_down_sync(0xffffffffu, qx, 1);
+                    const double qz = __shfl_down_sync(0xffffffffu, qx, 2);
+                    if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, qx, qy, qz, make_tag(st + 1, qx, qy, qz));
                 }
                 cstep[u] = st + 1;
                 pbuf ^= 1;
@@ -767,8 +776,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
 #pragma unroll
             for (int u = 0; u < TL; u++) {
                 const TrajDesc& d = descs[tb + u];
-                d.q[ik * n + my_body] = iq[u];
-                d.v[ik * n + my_body] = iv[u];
+                d.q[ik * n + my_body] = TL > 1 ? sh.iqv[tb + u][0][lane] : iq[u];
+                d.v[ik * n + my_body] = TL > 1 ? sh.iqv[tb + u][1][lane] : iv[u];
             }
         }
     }

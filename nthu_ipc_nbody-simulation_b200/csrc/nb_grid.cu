@@ -65,10 +65,33 @@
 #include "nb_internal.h"
 #include "nb_math.cuh"
 
+// Register re-allocation between the warp roles (setmaxnreg, sm_90a+).  With 10 warps two of the four schedulers hold three
+// warps, so no thread can have more than 168 registers, and at 166 ptxas serialises the four pair chains of a record
+// (its own stall counts: 363 cycles per 8 pairs, 416 - 462 in the two-system kernel).  The block is launched with 12 warps
+// instead (the helper warp group 8 - 11: observer, producer, two idle warps), the helpers shrink to NB_GRID_REG_HELPER
+// registers and the eight compute warps grow to NB_GRID_REG_COMPUTE: 320 cycles per 8 pairs, pairs phase 2860 -> 2430 clk
+// (FP64 pipe 76 -> 90 % busy in that phase), b1024 3.38 -> 3.30 us per step, 1-GPU solve 1.23 -> 1.19 s (224 / 56: 3.36 /
+// 1.205, the observer spills; 216 / 72: 3.30 / 1.19; 200 / 104: 3.37 / 1.19).  The pool is what the launch allocated: the
+// increase WAITS until 8 x compute + 4 x helper <= 12 x 168 - a larger request hangs the kernel.  0 = off (10 warps).
+#ifndef NB_GRID_REG_COMPUTE
+#define NB_GRID_REG_COMPUTE 208
+#endif
+#ifndef NB_GRID_REG_HELPER
+#define NB_GRID_REG_HELPER 88
+#endif
+static_assert(NB_GRID_REG_COMPUTE == 0 || (8 * NB_GRID_REG_COMPUTE + 4 * NB_GRID_REG_HELPER <= 12 * 168 && NB_GRID_REG_COMPUTE % 8 == 0 &&
+                                           NB_GRID_REG_HELPER % 8 == 0 && NB_GRID_REG_HELPER >= 24 && NB_GRID_REG_COMPUTE <= 232),
+              "setmaxnreg: the compute warps' increase must fit into what the helper warps release");
+
 namespace nb {
 
 namespace {
 
+constexpr bool REGALLOC = NB_GRID_REG_COMPUTE > 0;
+#ifndef NB_GRID_UNROLL
+#define NB_GRID_UNROLL 2
+#endif
+constexpr int PAIR_UNROLL = NB_GRID_UNROLL;  // records per trip of the pair loop (4 pairs each)
 constexpr int GB = 8;            // bodies per block
 constexpr int BPW = 4;           // bodies per compute warp
 constexpr int MAX_NJ = 8;        // compute warps = 2 body groups x NJ j-parts (NJ = 4 or 8); then the observer warp and
@@ -251,7 +274,7 @@ __device__ NB_GRID_VALIDATE_ATTR bool validate_stage(double* pos, const double* 
 // warps that take two j-parts each, an observer warp, a producer thread) and runs at its own pace - two independent "virtual
 // blocks" per SM that share nothing but the FP64 pipe.  Without SPLIT one warp set steps the T systems in turn (lock step).
 template <int MATH, int T, int NJ, bool PROFILE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 32 * T * (NJ + 2) : 32 * (2 * NJ + 2), 1)
+__global__ void __launch_bounds__(SPLIT ? 32 * T * (NJ + 2) : (REGALLOC ? 384 : 32 * (2 * NJ + 2)), 1)
 grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ fst, double* __restrict__ gbuf,
                  long long* __restrict__ prof, int* __restrict__ status, int R, int delay_clk, int delay_single, int adapt_up,
                  int adapt_down) {
@@ -261,7 +284,8 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     const int c = blockIdx.x;
     const int n = descs[0].n;
     constexpr int PPW = SPLIT ? 2 : 1;  // j-parts per compute warp
-    constexpr int NCW = 2 * NJ / PPW, NSET = SPLIT ? T : 1, W_OBS = NSET * NCW, W_PROD = W_OBS + NSET, GT = 32 * (W_PROD + NSET), RQ = 32 * NJ;
+    constexpr int NCW = 2 * NJ / PPW, NSET = SPLIT ? T : 1, W_OBS = NSET * NCW, W_PROD = W_OBS + NSET, RQ = 32 * NJ;
+    constexpr int GT = (REGALLOC && !SPLIT) ? 384 : 32 * (W_PROD + NSET);  // threads of the block (REGALLOC: two idle warps)
     constexpr int TL = SPLIT ? 1 : T;  // systems per warp set: a role warp handles systems tb .. tb + TL - 1
     const int RS = (R + RPAD - 1) / RPAD * RPAD;  // records per stage in shared memory (tail beyond R: zero mass, never copied)
     // per system: pos[2][RS] records {x, y, z, tag} then gm[2][RS]
@@ -366,7 +390,17 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         return true;
     };
 
-    if (warp >= W_PROD) {
+#if NB_GRID_REG_COMPUTE > 0
+    if (!SPLIT) {  // warp-group aligned: warps 0-3 and 4-7 compute, 8-11 help
+        if (warp >= W_OBS)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_HELPER));
+        else
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_COMPUTE));
+    }
+#endif
+    if (warp >= W_PROD + NSET) {
+        // idle warps of the helper warp group (REGALLOC only)
+    } else if (warp >= W_PROD) {
         // ------------------------------------------------------------------ PRODUCER thread
         const int tb = SPLIT ? warp - W_PROD : 0;
         if (lane == 0) {
@@ -648,7 +682,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                             const double* p = pos + 4 * (body0 + i);
                             xi[i] = p[0], yi[i] = p[1], zi[i] = p[2];
                         }
-#pragma unroll 2
+#pragma unroll PAIR_UNROLL
                         for (int r = 32 * jp + lane; r < RS; r += RQ) {
                             // conflict-free LDS.128 pair: lanes with bit 2 set read the record's second half first
                             const double2 A = *reinterpret_cast<const double2*>(pos + 4 * r + 2 * hsel);
@@ -817,7 +851,7 @@ WsLayout ws_layout(int n, int T) {
 
 template <int MATH, int T, int NJ, bool SPLIT = false>
 int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, cudaStream_t stream) {
-    constexpr int GT = SPLIT ? 32 * T * (NJ + 2) : 32 * (2 * NJ + 2);
+    constexpr int GT = SPLIT ? 32 * T * (NJ + 2) : (REGALLOC ? 384 : 32 * (2 * NJ + 2));
     const int C = padded_blocks(n, cs);
     const size_t smem = smem_for(n, T, cs);
     const WsLayout w = ws_layout(n, MAX_T);  // one layout for every T: the status word has a fixed place

@@ -88,6 +88,12 @@ namespace nb {
 namespace {
 
 constexpr bool REGALLOC = NB_GRID_REG_COMPUTE > 0;
+// With the helper warp group in place (REGALLOC) and several systems in lock step, one of its idle warps is the INTEGRATOR: the
+// compute warps only ARRIVE at the barrier behind their reduction and go on to the next system, the integrator waits there,
+// sums the j-parts, integrates and publishes.  NB_GRID_INTEGRATOR=0 (and always with one system): warp 0 of the compute set.
+#ifndef NB_GRID_INTEGRATOR
+#define NB_GRID_INTEGRATOR 1
+#endif
 #ifndef NB_GRID_UNROLL
 #define NB_GRID_UNROLL 2
 #endif
@@ -287,6 +293,10 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
     constexpr int NCW = 2 * NJ / PPW, NSET = SPLIT ? T : 1, W_OBS = NSET * NCW, W_PROD = W_OBS + NSET, RQ = 32 * NJ;
     constexpr int GT = (REGALLOC && !SPLIT) ? 384 : 32 * (W_PROD + NSET);  // threads of the block (REGALLOC: two idle warps)
     constexpr int TL = SPLIT ? 1 : T;  // systems per warp set: a role warp handles systems tb .. tb + TL - 1
+    // integrator warp = W_PROD + NSET, for several systems in lock step only: with one system nothing else could use the time, and
+    // the hand-over costs it 130 clk per step (measured: 3.30 -> 3.43 us; two systems: 1-GPU solve 1.18 -> 1.14 s)
+    constexpr bool USE_INT = REGALLOC && !SPLIT && TL > 1 && NB_GRID_INTEGRATOR;
+    constexpr int BAR_INT = 2;  // named barriers BAR_INT + t: the compute warps arrive, the integrator waits (32 * (NCW + 1) threads)
     const int RS = (R + RPAD - 1) / RPAD * RPAD;  // records per stage in shared memory (tail beyond R: zero mass, never copied)
     // per system: pos[2][RS] records {x, y, z, tag} then gm[2][RS]
     auto s_pos = [&](int t, int stage) { return smem + (size_t)t * 10 * RS + (size_t)stage * 4 * RS; };
@@ -390,16 +400,72 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         return true;
     };
 
+    // two branches, each behind its own setmaxnreg (warp-group aligned: warps 0-3 and 4-7 compute, 8-11 help)
+    if (warp >= W_OBS) {
 #if NB_GRID_REG_COMPUTE > 0
-    if (!SPLIT) {  // warp-group aligned: warps 0-3 and 4-7 compute, 8-11 help
-        if (warp >= W_OBS)
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_HELPER));
-        else
-            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_COMPUTE));
-    }
+    if (!SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_HELPER));
 #endif
-    if (warp >= W_PROD + NSET) {
-        // idle warps of the helper warp group (REGALLOC only)
+    if (USE_INT && warp == W_PROD + NSET) {
+        // ------------------------------------------------------------------ INTEGRATOR warp (lane < 24: body 8c + lane/3, component lane%3)
+        const int ib = lane / 3, ik = lane - 3 * ib, my_body = c * GB + ib;
+        const bool integ = lane < 3 * GB, mine = integ && my_body < n;
+        int istep[TL], ibegin[TL], iend[TL];
+        bool iact[TL];
+        double iq[TL], iv[TL];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < TL; u++) {
+            const TrajDesc& d = descs[u];
+            istep[u] = ibegin[u] = d.step_begin, iend[u] = d.step_end;
+            iact[u] = !((d.kind >= NB_KIND_Q2) && d.ev->hit_step != -2);
+            iq[u] = mine ? d.q[ik * n + my_body] : 0.0;
+            iv[u] = mine ? d.v[ik * n + my_body] : 0.0;
+            any |= iact[u];
+        }
+        bool aborted = false;
+        while (any && !aborted) {
+#pragma unroll
+            for (int u = 0; u < TL; u++) {
+                if (!iact[u]) continue;
+                const int t = u, st = istep[u], stage = st & 1;
+                // the observer's verdict on step st, as the compute warps read it: on STOP they do not come to the barrier
+                const int flags = wait_bar(&sh.obs[t][stage], (uint32_t)((st - ibegin[u]) >> 1) & 1u) ? (int)sh.flags[t][stage] : (int)FLAG_STOP;
+                if (flags & FLAG_STOP) {
+                    iact[u] = false;
+                    continue;
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(BAR_INT + t), "n"(32 * (NCW + 1)) : "memory");  // the eight warps' sums are in sh.part
+                if (sh.abort) {
+                    aborted = true;
+                    break;
+                }
+                // a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one tagged sector, unfenced
+                if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
+                if (integ) {
+                    const double* p = &sh.part[t][stage][(ib >> 2) * NJ][3 * (ib & 3) + ik];
+                    double a = p[0];
+#pragma unroll
+                    for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
+                    if (my_body < n) kick_drift(a, iv[u], iq[u]);
+                }
+                const double qy = __shfl_down_sync(0xffffffffu, iq[u], 1);
+                const double qz = __shfl_down_sync(0xffffffffu, iq[u], 2);
+                if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, iq[u], qy, qz, make_tag(st + 1, iq[u], qy, qz));
+                istep[u] = st + 1;
+            }
+            any = false;
+#pragma unroll
+            for (int u = 0; u < TL; u++) any |= iact[u];
+        }
+        if (mine) {
+#pragma unroll
+            for (int u = 0; u < TL; u++) {
+                descs[u].q[ik * n + my_body] = iq[u];
+                descs[u].v[ik * n + my_body] = iv[u];
+            }
+        }
+    } else if (warp >= W_PROD + NSET) {
+        // idle warp(s) of the helper warp group (REGALLOC only)
     } else if (warp >= W_PROD) {
         // ------------------------------------------------------------------ PRODUCER thread
         const int tb = SPLIT ? warp - W_PROD : 0;
@@ -459,7 +525,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 }
             }
         }
-    } else if (warp >= W_OBS) {
+    } else {
         // ------------------------------------------------------------------ OBSERVER warp
         const int tb = SPLIT ? warp - W_OBS : 0;
         ObsState os[TL];
@@ -581,7 +647,11 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 }
             }
         }
+    }
     } else {
+#if NB_GRID_REG_COMPUTE > 0
+        if (!SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NB_GRID_REG_COMPUTE));
+#endif
         // ------------------------------------------------------------------ COMPUTE warps
         const int tb = SPLIT ? warp / NCW : 0;          // the warp set's (first) system
         const int cw = warp - tb * NCW, ctid = tid - tb * 32 * NCW;  // warp / thread index inside the set
@@ -593,7 +663,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         const int ib = lane / 3, ik = lane - 3 * ib;
         const int my_body = c * GB + ib;
         const bool integ = cw == 0 && lane < 3 * GB;
-        double (*spart)[2 * MAX_NJ][3 * BPW] = sh.part[tb];
+
         int cstep[TL], cbegin[TL], cend[TL];
         bool cact[TL];
         double iq[TL], iv[TL];
@@ -623,7 +693,6 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
             c0 = clock64();
         }
-        int pbuf = 0;
         bool aborted = false;
 
         while (any && !aborted) {
@@ -720,7 +789,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                         m2 += __shfl_xor_sync(0xffffffffu, m2, o);
                     }
                     if ((lane & 7) == 0) {
-                        double* dstp = &spart[pbuf][bg * NJ + jp][3 * (lane >> 3)];
+                        double* dstp = &sh.part[t][stage][bg * NJ + jp][3 * (lane >> 3)];
                         dstp[0] = m0, dstp[1] = m1, dstp[2] = m2;
                     }
                 };
@@ -755,17 +824,20 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                 }
                 if (PPW == 1) butterfly_store(part0);
                 tick(3);
-                compute_bar<32 * NCW>(bar_id);
+                if (USE_INT)  // the integrator warp takes it from here
+                    asm volatile("bar.arrive %0, %1;" ::"r"(BAR_INT + t), "n"(32 * (NCW + 1)) : "memory");
+                else
+                    compute_bar<32 * NCW>(bar_id);
                 if (sh.abort) {  // an exchange wait timed out somewhere in this block
                     aborted = true;
                     break;
                 }
                 // (4) warp 0: a = sum of the j-parts; v += a*dt; q += v*dt (nbody.cc:77-88); publish the body as one
                 //     tagged sector {x, y, z, step}, unfenced
-                if (cw == 0) {
+                if (!USE_INT && cw == 0) {
                     if (lane == 0) mbar_arrive(&sh.trig[t][(st + 1) & 1]);  // producer trigger: everybody publishes within ~150 clk
                     if (integ) {
-                        const double* p = &spart[pbuf][(ib >> 2) * NJ][3 * (ib & 3) + ik];
+                        const double* p = &sh.part[t][stage][(ib >> 2) * NJ][3 * (ib & 3) + ik];
                         double a = p[0];
 #pragma unroll
                         for (int j = 1; j < NJ; j++) a += p[j * 3 * BPW];  // fixed order: deterministic
@@ -783,7 +855,6 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
                     if (integ && ik == 0) st_sector(g_rec(t, st + 1) + 4 * (size_t)my_body, qx, qy, qz, make_tag(st + 1, qx, qy, qz));
                 }
                 cstep[u] = st + 1;
-                pbuf ^= 1;
                 tick(4);
             }
             any = false;
@@ -806,7 +877,7 @@ grid_traj_kernel(const TrajDesc* __restrict__ descs, const double* __restrict__ 
         }
         if (PROFILE && n_stale) atomicAdd((unsigned long long*)&prof[5], n_stale);
         // write back
-        if (integ && my_body < n) {
+        if (!USE_INT && integ && my_body < n) {
 #pragma unroll
             for (int u = 0; u < TL; u++) {
                 const TrajDesc& d = descs[tb + u];
@@ -865,7 +936,7 @@ int launch_t(int n, int cs, const TrajDesc* descs, const double* fst, void* ws, 
     // behind the pair loop of the other and a longer delay (fewer stale records, fewer polls) wins (measured: b1024
     // four-trajectory solve on one GPU 2.33 s at 900, 2.00 s at 2600)
     // SPLIT: every system has its own warp set and timeline, i.e. behaves like a single system
-    static const int delay_clk_env = (T == 1 || SPLIT) ? env_int("NB_GRID_DELAY", 900) : env_int("NB_GRID_DELAY2", 3400);
+    static const int delay_clk_env = (T == 1 || SPLIT) ? env_int("NB_GRID_DELAY", 900) : env_int("NB_GRID_DELAY2", 3000);
     static const int delay_single_env = env_int("NB_GRID_DELAY", 900);
     auto kern = profile ? grid_traj_kernel<MATH, T, NJ, true, SPLIT> : grid_traj_kernel<MATH, T, NJ, false, SPLIT>;
     NB_CUDA(cudaMemsetAsync(ws, 0, w.gbuf_bytes, stream));  // tag 0 = no step

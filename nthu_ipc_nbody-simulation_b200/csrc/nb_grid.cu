@@ -28,7 +28,8 @@
 //     TMA overwrites the step s-2 stage in shared memory) only after its step s-1 data reached everybody, and
 //     every block publishes step s-1 only after it finished reading step s-2.
 //
-// Warp roles (320 threads):
+// Warp roles (384 threads = 12 warps: compute warp groups 0-3 and 4-7, helper warp group 8-11; registers are re-allocated
+// between them with setmaxnreg, see NB_GRID_REG_COMPUTE below):
 //   * 8 COMPUTE warps = 2 body groups x 4 j-quarters: warp w holds bodies 8c + 4(w>>2) .. +3 in registers and
 //     takes records 128k + 32(w&3) + lane: four i-bodies share every j record read from shared memory
 //     (conflict-free LDS.128 pairs: lanes with bit 2 set read the record's second half first).  A transposing
@@ -41,14 +42,16 @@
 //     the next stage, so the pair loop is oblivious to devices.  The one step on which a device is destroyed
 //     (its mass was written speculatively) is redone by the compute warps with the corrected column.
 //   * 1 PRODUCER thread: arms the stage's mbarrier with the expected byte count and issues the TMA copies.
+//   * lock-step launches (two systems per launch): 1 INTEGRATOR warp takes the serial tail of a step (sum of the j-parts,
+//     integration, publication) from warp 0, the compute warps only arrive at its barrier and go on to the other system.
 //
 // Spins are bounded (clock64) and raise `status`; co-residency comes from the cooperative launch
 // (grid <= SM count, 1 block/SM).
 //
-// Measured on B200, b1024 (profiles/r01_grid_exchange_v2.md): 3.2-3.4 us/step for one system (copy delay 600-1200
-// clk, clusters of 2 or 4) against 4.4-4.9 us for the previous exchange (per-producer sentinel poll, then LDG
-// fetch warps: two dependent L2 round trips per step); in-kernel phases per step at 1.96 GHz: copy 1775 clk
-// (delay 900 + TMA round trip), validate 620, pairs 3200 (FP64 floor 2048), butterfly 515, integrate+publish 440.
+// Measured on B200, b1024 (profiles/r01_grid_exchange_v2.md, r02_grid_exchange.md): 3.30 us/step for one system (round 1,
+// step-only tags: 3.2-3.4) against 4.4-4.9 us for the first exchange (per-producer sentinel poll, then LDG
+// fetch warps: two dependent L2 round trips per step); in-kernel phases per step at 1.96 GHz: copy wait 1450 clk
+// (closed-loop delay + TMA round trip), validate 1130, pairs 2430 (FP64 floor 2184), butterfly 415, integrate+publish 550.
 // Tried and measured worse: validating inside the pair loop (a vote per record batch serialises the loop),
 // optimistic pair loop + redo on a stale record (a redone block is late, all others find it stale: cascade),
 // per-block adaptive delays (creep up together), rotating the tag slot for conflict-free validation loads.

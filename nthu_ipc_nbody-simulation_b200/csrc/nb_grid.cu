@@ -1104,7 +1104,7 @@ bool grid_traj_supported(int gpu, int n, int n_traj) {
 void grid_traj_warm() {
     cudaFuncAttributes fa;
     (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 1, 4, false, false>);
-    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 2, 4, false, true>);
+    (void)cudaFuncGetAttributes(&fa, grid_traj_kernel<MATH_FAST, 2, 4, false, false>);  // two systems in lock step (default)
 }
 
 // device address of the status word of a workspace: 0 = ok, 1 = an exchange spin timed out (read after the stream is idle)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 L=${1:-gpurun_out/hw5_wall.log}; : > $L
 T=tests/golden/testcases
 P=nthu_ipc_nbody-simulation_b200
-t() { local s=$(date +%s.%N); "$@" >> $L 2>&1; local rc=$?; local e=$(date +%s.%N); echo "wall $(echo "$e - $s" | bc) s rc=$rc :: $*" >> $L; }
+t() { local s=$(date +%s.%N); "$@" >> $L 2>&1; local rc=$?; local e=$(date +%s.%N); echo "wall $(python3 -c "print(round($e - $s, 3))") s rc=$rc :: $*" >> $L; }
 nvidia-smi -L >> $L
 for rep in 1 2 3; do
 t $P/cuda_floor

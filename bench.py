@@ -270,6 +270,28 @@ def make_system(nb, kind, system, rank, world, dev):
     return nb.ShardedSystem(system, rank=rank, world=world, device=dev)
 
 
+def reference_gpu_block(nb):
+    """BASELINE.md section 4 item 5 (opt-in, --reference-gpu): the reference's OWN GPU program, hw5.cu rebuilt for sm_100a
+    (oracle/_ref/hw5_gpu, built from /root/reference by oracle/Makefile), as a process on b1024.  It hard-codes GPUs 0 and 1
+    (hw5.cu:558-567), so it needs two visible GPUs.  Nothing of this repository is loaded by that process."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "hw5_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/hw5_gpu was not built (reference tree or nvcc missing at build time)"}
+    if nb.device_count() < 2:
+        return {"unavailable": "needs two visible GPUs (hw5.cu:558-567 uses ordinals 0 and 1)"}
+    inp, gold = os.path.join(CASES, "b1024.in"), open(os.path.join(CASES, "b1024.out"), "rb").read()
+    out = "/tmp/bench_refgpu_%d.out" % os.getpid()
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run([exe, inp, out], capture_output=True, timeout=600)
+    except subprocess.TimeoutExpired:
+        return {"wall_s": None, "timeout_s": 600}
+    wall = time.perf_counter() - t0
+    same = r.returncode == 0 and os.path.exists(out) and open(out, "rb").read() == gold
+    return {"wall_s": wall, "rc": r.returncode, "byte_identical_to_golden": bool(same), "gpus": 2,
+            "what": "process wall of the reference's hw5.cu (nvcc -std=c++11 -O3, -arch=sm_61 replaced by sm_100a) on b1024.in"}
+
+
 def hw5_process_block(nb):
     """The real `hw5 <input> <output>` PROCESS on b1024 (BASELINE metric (i)) next to the floor of any CUDA process on
     this box (driver initialisation + one context + one empty kernel, tools/microbench/cuda_floor.cu)."""
@@ -555,6 +577,8 @@ def run_ours(args):
             b1024["torn_records_detected"] = nb.grid_torn_records()
         if rank == 0 and not args.no_hw5_process:
             b1024["hw5_process"] = hw5_process_block(nb)
+        if rank == 0 and args.reference_gpu:
+            b1024["reference_hw5_cu_process"] = reference_gpu_block(nb)
         barrier()
 
     # ---- config C4: the synthetic ensemble ----------------------------------------------------------
@@ -625,6 +649,13 @@ def cpu_extras(nb, np, system, args):
                           "what": "full b20.in run of the unmodified samples/nbody.cc (query 1 + query 2), output lines 1-2 equal the golden"}
     except Exception as e:  # noqa: BLE001
         ex["b20_full"] = {"error": str(e)}
+    if getattr(args, "cpu_b100_full", False):  # about three minutes of one host core, opt-in
+        try:
+            dt, pairs, kind = reference_run("b100")
+            ex["b100_full"] = {"seconds": dt, "pairs_per_s": pairs / dt, "cores": 1, "kind": kind,
+                               "what": "full b100.in run of the unmodified samples/nbody.cc (query 1 + query 2), output lines 1-2 equal the golden"}
+        except Exception as e:  # noqa: BLE001
+            ex["b100_full"] = {"error": str(e)}
     exe = os.path.join(ROOT, "oracle", "_ref", "nbody_steps200")
     if os.path.exists(exe):
         out = "/tmp/bench_w200_%d.out" % os.getpid()
@@ -758,6 +789,10 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-hw5-process", action="store_true")
     ap.add_argument("--no-oracle-full-step", action="store_true")
+    ap.add_argument("--reference-gpu", action="store_true",
+                    help="also run the reference's own hw5.cu (rebuilt for sm_100a, needs two visible GPUs) on b1024 as a process")
+    ap.add_argument("--cpu-b100-full", action="store_true",
+                    help="also time the full b100 run of the unmodified samples/nbody.cc (about 3 minutes of one host core)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

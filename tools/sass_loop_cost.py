@@ -91,7 +91,6 @@ def main():
             if n < min_fp64:
                 continue
             ops = collections.Counter(o.split(".")[0] for _, o, _, _ in seg)
-            extra = 0.7 * ops["SHFL"] + 0.5 * ops["MUFU"] / 1.0 * 0.125 * 8 * 0.125
             acc3 = sum(v for (o, d, f), v in hist.items() if o == "DFMA" and d == 3)
             acc3_free = sum(v for (o, d, f), v in hist.items() if o == "DFMA" and d == 3 and f >= 1)
             print("  loop 0x%x..0x%x: %d instr, %d FP64 (%d three-operand DFMA, %d of them with a reuse hit), FP64 pipe cycles %d "

@@ -65,3 +65,19 @@ def test_symmetric_kernels_use_tma_and_no_atomics_on_the_accumulation(sass):
             assert "UBLKCP" in body and "SHFL.IDX" in body, name
             assert "ATOM" not in body.replace("ATOMS.CAST", ""), name   # partial rows + fixed-order sums, never atomics
             assert len(re.findall(r"\bDFMA\b", body)) >= 400, name
+
+
+def test_grid_pair_loop_schedule_did_not_regress():
+    """The pair loop of the grid kernel is the one place where ptxas' register allocation decides the speed: with the role
+    branches not dominated by their setmaxnreg it once scheduled 668 stall cycles per 8 pairs instead of 320 (4.2 us per step
+    instead of 3.3).  Guard: the production instantiations (one system; two systems in lock step) stay below 340."""
+    import sys
+    obj = os.path.join(ROOT, "nthu_ipc_nbody-simulation_b200", "_build", "nb_grid.o")
+    if not os.path.exists(obj):
+        pytest.skip("object file not kept")
+    for inst in ("ILi0ELi1ELi4ELb0ELb0", "ILi0ELi2ELi4ELb0ELb0"):
+        out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sass_loop_stalls.py"), obj, inst, "120"]).decode()
+        loops = [(int(m.group(1)), int(m.group(2))) for m in re.finditer(r"(\d+) FP64, sum of stall counts (\d+)", out)]
+        pair_loops = [s for n, s in loops if n == 128]  # 8 pairs x 16 FP64 instructions per trip
+        assert pair_loops, out
+        assert max(pair_loops) <= 340, (inst, pair_loops)
